@@ -1,0 +1,14 @@
+"""evavos_b200 - the STCN/MiVOS space-time memory read of EVA-VOS on B200 (sm_100a).
+
+Host code is Python/PyTorch (device memory, streams, torch.distributed); the arithmetic is in
+hand-written CUDA behind the C ABI of include/evavos.h (libevavos_sm100.so, loaded with ctypes).
+Importing the package does not load the library; the first kernel call does, and fails loudly
+if it has not been built (no CPU fallback).
+"""
+from . import _lib
+from ._lib import EvavosError
+from .aggregate import aggregate_wbg
+from .memory_bank import MemoryBank
+from .memory_reader import EvalMemoryReader, TopKAffinity, memory_read
+
+__all__ = ["EvavosError", "aggregate_wbg", "MemoryBank", "EvalMemoryReader", "TopKAffinity", "memory_read", "_lib"]

@@ -1,0 +1,27 @@
+"""aggregate_wbg with the reference's signature (mivos/model/aggregate.py:22-37), one fused kernel."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def aggregate_wbg(prob: torch.Tensor, keep_bg: bool = False, hard: bool = False) -> torch.Tensor:
+    """prob (K,1,h,w) fp32 object probabilities -> (K+1,1,h,w) if keep_bg else (K,1,h,w).
+
+    Background = prod_k (1 - p_k); all channels clamped to [1e-7, 1-1e-7], turned into logits
+    (x1000 when ``hard``) and soft-maxed over the object axis.
+    """
+    lib = _lib.load()
+    if not prob.is_cuda:
+        raise RuntimeError("aggregate_wbg: CUDA tensor required (no CPU path in evavos_b200)")
+    if prob.dim() != 4:
+        raise ValueError("prob must be (K,1,h,w)")
+    k, c, h, w = prob.shape
+    p = prob.to(torch.float32).contiguous()
+    npix = c * h * w
+    out = torch.empty(((k + 1) if keep_bg else k, c, h, w), dtype=torch.float32, device=prob.device)
+    with torch.cuda.device(prob.device):
+        _lib.check(lib.evavos_aggregate_wbg(p.data_ptr(), out.data_ptr(), k, npix, int(bool(keep_bg)), int(bool(hard)),
+                                            _lib.current_stream_ptr(prob.device)))
+    return out

@@ -1,0 +1,389 @@
+// extern "C" entry points of libevavos_sm100.so (see include/evavos.h for the contract).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace evavos {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return EVAVOS_ERR_CUDA;
+}
+
+namespace {
+
+int device_sm_count(int* n_sm) {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0;
+    EVAVOS_CUDA_OK(cudaGetDevice(&dev));
+    int major = 0;
+    EVAVOS_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) {
+      set_error("libevavos_sm100 needs an sm_100 (B200) device, found compute capability major %d", major);
+      return EVAVOS_ERR_UNSUPPORTED;
+    }
+    EVAVOS_CUDA_OK(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev));
+  }
+  *n_sm = cached;
+  return EVAVOS_OK;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+bool use_tensor_path(const EvavosMemReadArgs& a) {
+  if (a.path == EVAVOS_PATH_SIMT) return false;
+  return a.bank.CK == 64 && a.bank.key_tiles != nullptr && a.bank.key_maxnorm != nullptr;
+}
+
+struct Carve {
+  SelectBuffers sb;
+  int32_t* idx;
+  float* weight;
+  size_t total;
+};
+
+// Lays the workspace out; with base == nullptr only the size is computed.
+Carve carve_workspace(const EvavosMemReadArgs& a, int n_chunks, uint8_t* base) {
+  Carve c;
+  memset(&c, 0, sizeof(c));
+  const int64_t mt = ceil_div(a.n_query, 128);
+  const int64_t nq_pad = mt * 128;
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> uint8_t* {
+    uint8_t* p = base ? base + off : nullptr;
+    off += align_up(bytes, 1024);
+    return p;
+  };
+  c.sb.q_pm = reinterpret_cast<float*>(take(sizeof(float) * nq_pad * a.bank.CK));
+  c.sb.q_tiles = take((size_t)mt * kTileBytes);
+  c.sb.q_maxnorm = reinterpret_cast<float*>(take(sizeof(float)));
+  c.sb.class_max = reinterpret_cast<float*>(take(n_chunks > 0 ? sizeof(float) * (size_t)n_chunks * nq_pad * 128 : 0));
+  c.sb.tau = reinterpret_cast<float*>(take(sizeof(float) * nq_pad));
+  c.sb.cand_cnt = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * nq_pad));
+  c.sb.cand = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * nq_pad * kCandCap));
+  c.sb.work_list = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * nq_pad));
+  c.sb.work_cnt = reinterpret_cast<int32_t*>(take(sizeof(int32_t)));
+  c.idx = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * a.n_query * a.top_k));
+  c.weight = reinterpret_cast<float*>(take(sizeof(float) * a.n_query * a.top_k));
+  c.total = off + 1024;  // slack for aligning the caller's pointer
+  return c;
+}
+
+int validate_bank(const EvavosBankShadow* b) {
+  if (!b) { set_error("bank is NULL"); return EVAVOS_ERR_INVALID; }
+  if (b->CK <= 0 || b->CK > 64 || (b->CK % 8) != 0) {
+    set_error("CK=%d unsupported (need a multiple of 8, <= 64)", b->CK);
+    return EVAVOS_ERR_UNSUPPORTED;
+  }
+  if (b->K < 0 || b->CV < 0 || b->capacity_pos <= 0) { set_error("bad bank sizes"); return EVAVOS_ERR_INVALID; }
+  if (b->val_dtype != EVAVOS_F32 && b->val_dtype != EVAVOS_BF16) {
+    set_error("val_dtype=%d unsupported", b->val_dtype);
+    return EVAVOS_ERR_UNSUPPORTED;
+  }
+  return EVAVOS_OK;
+}
+
+int validate_read(const EvavosMemReadArgs* a) {
+  if (!a) { set_error("args is NULL"); return EVAVOS_ERR_INVALID; }
+  int rc = validate_bank(&a->bank);
+  if (rc) return rc;
+  if (!a->bank.key_pm) { set_error("bank.key_pm is NULL"); return EVAVOS_ERR_INVALID; }
+  if (!a->query || a->n_query <= 0 || a->n_pos <= 0) { set_error("empty query or bank"); return EVAVOS_ERR_INVALID; }
+  if (a->n_pos > a->bank.capacity_pos) { set_error("n_pos exceeds bank capacity"); return EVAVOS_ERR_INVALID; }
+  if (a->n_pos >= (int64_t)1 << 31) { set_error("n_pos must fit int32"); return EVAVOS_ERR_UNSUPPORTED; }
+  if (a->top_k <= 0 || a->top_k > EVAVOS_MAX_TOPK) {
+    set_error("top_k=%d unsupported (1..%d)", a->top_k, EVAVOS_MAX_TOPK);
+    return EVAVOS_ERR_UNSUPPORTED;
+  }
+  if (a->n_pos < a->top_k) {
+    set_error("selected index k out of range (THW=%lld < top_k=%d)", (long long)a->n_pos, a->top_k);
+    return EVAVOS_ERR_TOPK_RANGE;
+  }
+  if (a->path == EVAVOS_PATH_TENSOR && !(a->bank.CK == 64 && a->bank.key_tiles && a->bank.key_maxnorm)) {
+    set_error("tensor path needs CK == 64, key_tiles and key_maxnorm");
+    return EVAVOS_ERR_UNSUPPORTED;
+  }
+  if (a->readout && (!a->bank.val_pm || a->bank.K <= 0)) { set_error("readout requested without values"); return EVAVOS_ERR_INVALID; }
+  return EVAVOS_OK;
+}
+
+int resolve_sm(const EvavosMemReadArgs* a, int* n_sm) {
+  if (a->n_sm > 0) { *n_sm = a->n_sm; return EVAVOS_OK; }
+  return device_sm_count(n_sm);
+}
+
+}  // namespace
+}  // namespace evavos
+
+using namespace evavos;
+
+extern "C" {
+
+int evavos_abi_version(void) { return EVAVOS_ABI_VERSION; }
+const char* evavos_last_error(void) { return g_err; }
+size_t evavos_sizeof_bank_shadow(void) { return sizeof(EvavosBankShadow); }
+size_t evavos_sizeof_memread_args(void) { return sizeof(EvavosMemReadArgs); }
+
+size_t evavos_key_tiles_bytes(int64_t capacity_pos) {
+  if (capacity_pos <= 0) return 0;
+  return (size_t)ceil_div(capacity_pos, kTilePos) * kTileBytes;
+}
+
+int evavos_bank_write_keys(const EvavosBankShadow* bank, const float* src, int64_t src_ch_stride, int64_t pos0,
+                           int64_t n_pos, float* dst_ref, int64_t dst_ref_ch_stride, evavos_stream_t stream) {
+  int rc = validate_bank(bank);
+  if (rc) return rc;
+  if (!src || !bank->key_pm || pos0 < 0 || n_pos < 0 || pos0 + n_pos > bank->capacity_pos) {
+    set_error("bank_write_keys: bad range [%lld, +%lld) for capacity %lld", (long long)pos0, (long long)n_pos,
+              (long long)bank->capacity_pos);
+    return EVAVOS_ERR_INVALID;
+  }
+  void* tiles = (bank->CK == 64) ? bank->key_tiles : nullptr;
+  return launch_write_keys(*bank, src, src_ch_stride, pos0, n_pos, dst_ref, dst_ref_ch_stride, bank->key_pm, tiles,
+                           bank->key_maxnorm, (cudaStream_t)stream);
+}
+
+int evavos_bank_write_values(const EvavosBankShadow* bank, const float* src, int64_t src_obj_stride,
+                             int64_t src_ch_stride, int64_t pos0, int64_t n_pos, float* dst_ref,
+                             int64_t dst_ref_obj_stride, int64_t dst_ref_ch_stride, evavos_stream_t stream) {
+  int rc = validate_bank(bank);
+  if (rc) return rc;
+  if (!src || !bank->val_pm || bank->K <= 0 || bank->CV <= 0 || pos0 < 0 || n_pos < 0 ||
+      pos0 + n_pos > bank->capacity_pos) {
+    set_error("bank_write_values: bad arguments");
+    return EVAVOS_ERR_INVALID;
+  }
+  return launch_write_values(*bank, src, src_obj_stride, src_ch_stride, pos0, n_pos, dst_ref, dst_ref_obj_stride,
+                             dst_ref_ch_stride, (cudaStream_t)stream);
+}
+
+size_t evavos_memread_workspace_bytes(const EvavosMemReadArgs* args) {
+  if (validate_read(args)) return 0;
+  int n_sm = 148;
+  if (args->n_sm > 0) n_sm = args->n_sm;
+  else if (device_sm_count(&n_sm)) n_sm = 148;
+  const int chunks = use_tensor_path(*args) ? score_pass_chunks(args->n_pos, args->n_query, n_sm) : 0;
+  return carve_workspace(*args, chunks, nullptr).total;
+}
+
+int evavos_memread(const EvavosMemReadArgs* a, evavos_stream_t stream) {
+  int rc = validate_read(a);
+  if (rc) return rc;
+  int n_sm = 0;
+  rc = resolve_sm(a, &n_sm);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tensor = use_tensor_path(*a);
+  const int chunks = tensor ? score_pass_chunks(a->n_pos, a->n_query, n_sm) : 0;
+  if (!a->workspace) { set_error("workspace is NULL"); return EVAVOS_ERR_WORKSPACE; }
+  uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(a->workspace), 1024));
+  const Carve probe = carve_workspace(*a, chunks, nullptr);
+  if ((int64_t)probe.total > a->workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %lld", probe.total, (long long)a->workspace_bytes);
+    return EVAVOS_ERR_WORKSPACE;
+  }
+  const Carve c = carve_workspace(*a, chunks, base);
+  const int CK = a->bank.CK;
+
+  // 1. query shadow: position-major fp32 rows (+ bf16 tile images, -|q|^2/2)
+  EvavosBankShadow qb = a->bank;
+  qb.capacity_pos = ceil_div(a->n_query, 128) * 128;
+  rc = launch_write_keys(qb, a->query, a->query_ch_stride, 0, a->n_query, nullptr, 0, c.sb.q_pm,
+                         tensor ? c.sb.q_tiles : nullptr, nullptr, st);
+  if (rc) return rc;
+
+  // 2. candidate generation
+  if (tensor) {
+    rc = launch_score_pass(1, c.sb.q_tiles, a->bank.key_tiles, a->n_pos, a->n_query, chunks, c.sb.class_max, nullptr,
+                           nullptr, nullptr, st);
+    if (rc) return rc;
+    rc = launch_threshold(c.sb.class_max, chunks, a->n_query, qb.capacity_pos, a->top_k, c.sb.q_tiles,
+                          a->bank.key_maxnorm, c.sb.tau, c.sb.cand_cnt, st);
+    if (rc) return rc;
+    rc = launch_score_pass(2, c.sb.q_tiles, a->bank.key_tiles, a->n_pos, a->n_query, chunks, nullptr, c.sb.tau,
+                           c.sb.cand, c.sb.cand_cnt, st);
+    if (rc) return rc;
+    rc = launch_overflow_list(c.sb.cand_cnt, a->n_query, c.sb.work_list, c.sb.work_cnt, st);
+    if (rc) return rc;
+    rc = launch_brute_select(a->bank.key_pm, c.sb.q_pm, CK, a->n_pos, a->n_query, a->top_k, c.sb.work_list,
+                             c.sb.work_cnt, c.sb.cand, c.sb.cand_cnt, n_sm, st);
+    if (rc) return rc;
+  } else {
+    rc = launch_brute_select(a->bank.key_pm, c.sb.q_pm, CK, a->n_pos, a->n_query, a->top_k, nullptr, nullptr,
+                             c.sb.cand, c.sb.cand_cnt, n_sm, st);
+    if (rc) return rc;
+  }
+
+  // 3. exact rescoring, top-k, softmax
+  int32_t* idx = a->topk_idx ? a->topk_idx : c.idx;
+  float* weight = a->topk_weight ? a->topk_weight : c.weight;
+  rc = launch_finalize(a->bank.key_pm, c.sb.q_pm, CK, a->n_query, a->top_k, c.sb.cand, c.sb.cand_cnt, idx, weight,
+                       a->topk_score, st);
+  if (rc) return rc;
+
+  // 4. sparse readout for all objects
+  if (a->readout) {
+    rc = launch_readout(a->bank, idx, weight, a->n_query, a->top_k, a->readout, a->readout_obj_stride,
+                        a->readout_ch_stride, st);
+    if (rc) return rc;
+  }
+  return EVAVOS_OK;
+}
+
+int evavos_readout(const EvavosBankShadow* bank, const int32_t* idx, const float* weight, int64_t n_query,
+                   int32_t top_k, float* out, int64_t out_obj_stride, int64_t out_ch_stride,
+                   evavos_stream_t stream) {
+  int rc = validate_bank(bank);
+  if (rc) return rc;
+  if (!bank->val_pm || !idx || !weight || !out || n_query <= 0 || top_k <= 0 || top_k > EVAVOS_MAX_TOPK) {
+    set_error("readout: bad arguments");
+    return EVAVOS_ERR_INVALID;
+  }
+  return launch_readout(*bank, idx, weight, n_query, top_k, out, out_obj_stride, out_ch_stride, (cudaStream_t)stream);
+}
+
+int evavos_affinity_dense(const int32_t* idx, const float* weight, int64_t n_query, int32_t top_k, int64_t n_pos,
+                          float* dense, evavos_stream_t stream) {
+  if (!idx || !weight || !dense || n_query <= 0 || top_k <= 0 || n_pos <= 0) {
+    set_error("affinity_dense: bad arguments");
+    return EVAVOS_ERR_INVALID;
+  }
+  return launch_affinity_dense(idx, weight, n_query, top_k, n_pos, dense, (cudaStream_t)stream);
+}
+
+int evavos_aggregate_wbg(const float* prob, float* out, int32_t K, int64_t npix, int32_t keep_bg, int32_t hard,
+                         evavos_stream_t stream) {
+  if (!prob || !out || K <= 0 || npix < 0) {
+    set_error("aggregate_wbg: bad arguments");
+    return EVAVOS_ERR_INVALID;
+  }
+  return launch_aggregate(prob, out, K, npix, keep_bg, hard, (cudaStream_t)stream);
+}
+
+int evavos_topk_merge(const int32_t* cand_idx, const float* cand_score, int64_t n_query, int32_t n_cand,
+                      int32_t top_k, int32_t shard, int32_t n_shards, int64_t pos_per_frame, int32_t* out_idx,
+                      float* out_weight, float* out_score, int32_t* local_idx, evavos_stream_t stream) {
+  if (!cand_idx || !cand_score || n_query <= 0 || n_cand <= 0 || top_k <= 0 || top_k > EVAVOS_MAX_TOPK ||
+      n_shards <= 0 || shard < 0 || shard >= n_shards || pos_per_frame <= 0) {
+    set_error("topk_merge: bad arguments");
+    return EVAVOS_ERR_INVALID;
+  }
+  return launch_topk_merge(cand_idx, cand_score, n_query, n_cand, top_k, shard, n_shards, pos_per_frame, out_idx,
+                           out_weight, out_score, local_idx, (cudaStream_t)stream);
+}
+
+// ---- host-buffer form ---------------------------------------------------------------------
+namespace {
+struct HostScratch {
+  uint8_t* dev = nullptr;
+  size_t bytes = 0;
+};
+HostScratch g_scratch;
+}  // namespace
+
+int evavos_release_host_scratch(void) {
+  if (g_scratch.dev) {
+    cudaFree(g_scratch.dev);
+    g_scratch.dev = nullptr;
+    g_scratch.bytes = 0;
+  }
+  return EVAVOS_OK;
+}
+
+int evavos_memread_host(const float* mem_key, const float* query, const float* mem_value, int32_t K, int32_t CK,
+                        int32_t CV, int64_t n_pos, int64_t n_query, int32_t top_k, int32_t path, float* readout,
+                        int32_t* topk_idx, float* topk_weight, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+  if (!mem_key || !query || (readout && !mem_value) || n_pos <= 0 || n_query <= 0) {
+    set_error("memread_host: bad arguments");
+    return EVAVOS_ERR_INVALID;
+  }
+  EvavosMemReadArgs a;
+  memset(&a, 0, sizeof(a));
+  a.bank.capacity_pos = n_pos;
+  a.bank.K = readout ? K : 0;
+  a.bank.CK = CK;
+  a.bank.CV = CV;
+  a.bank.val_dtype = EVAVOS_F32;
+  a.n_pos = n_pos;
+  a.n_query = n_query;
+  a.query_ch_stride = n_query;
+  a.top_k = top_k;
+  a.path = path;
+  // placeholders so validate_read / workspace sizing see a complete description
+  a.bank.key_pm = reinterpret_cast<float*>(0x1000);
+  a.bank.key_tiles = (CK == 64) ? reinterpret_cast<void*>(0x1000) : nullptr;
+  a.bank.key_maxnorm = reinterpret_cast<float*>(0x1000);
+  a.bank.val_pm = readout ? reinterpret_cast<void*>(0x1000) : nullptr;
+  a.query = reinterpret_cast<const float*>(0x1000);
+  a.readout = readout ? reinterpret_cast<float*>(0x1000) : nullptr;
+  int rc = validate_read(&a);
+  if (rc) return rc;
+  const size_t ws = evavos_memread_workspace_bytes(&a);
+
+  const size_t b_key = sizeof(float) * (size_t)CK * n_pos;
+  const size_t b_q = sizeof(float) * (size_t)CK * n_query;
+  const size_t b_val = readout ? sizeof(float) * (size_t)K * CV * n_pos : 0;
+  const size_t b_out = readout ? sizeof(float) * (size_t)K * CV * n_query : 0;
+  const size_t b_tk = sizeof(float) * (size_t)n_query * top_k;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  const size_t o_key = take(b_key), o_q = take(b_q), o_val = take(b_val), o_out = take(b_out);
+  const size_t o_idx = take(b_tk), o_w = take(b_tk);
+  const size_t o_kpm = take(b_key), o_tiles = take(evavos_key_tiles_bytes(n_pos)), o_max = take(4);
+  const size_t o_vpm = take(b_val), o_ws = take(ws);
+  const size_t total = off + 1024;
+  if (g_scratch.bytes < total) {
+    evavos_release_host_scratch();
+    EVAVOS_CUDA_OK(cudaMalloc(&g_scratch.dev, total));
+    g_scratch.bytes = total;
+  }
+  uint8_t* d = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(g_scratch.dev), 1024));
+  cudaStream_t st = 0;
+  EVAVOS_CUDA_OK(cudaMemcpyAsync(d + o_key, mem_key, b_key, cudaMemcpyHostToDevice, st));
+  EVAVOS_CUDA_OK(cudaMemcpyAsync(d + o_q, query, b_q, cudaMemcpyHostToDevice, st));
+  if (readout) EVAVOS_CUDA_OK(cudaMemcpyAsync(d + o_val, mem_value, b_val, cudaMemcpyHostToDevice, st));
+  EVAVOS_CUDA_OK(cudaMemsetAsync(d + o_max, 0, 4, st));
+
+  a.bank.key_pm = reinterpret_cast<float*>(d + o_kpm);
+  a.bank.key_tiles = (CK == 64) ? (void*)(d + o_tiles) : nullptr;
+  a.bank.key_maxnorm = reinterpret_cast<float*>(d + o_max);
+  a.bank.val_pm = readout ? (void*)(d + o_vpm) : nullptr;
+  a.query = reinterpret_cast<const float*>(d + o_q);
+  a.readout = readout ? reinterpret_cast<float*>(d + o_out) : nullptr;
+  a.topk_idx = reinterpret_cast<int32_t*>(d + o_idx);
+  a.topk_weight = reinterpret_cast<float*>(d + o_w);
+  a.workspace = d + o_ws;
+  a.workspace_bytes = (int64_t)ws;
+
+  rc = evavos_bank_write_keys(&a.bank, reinterpret_cast<const float*>(d + o_key), n_pos, 0, n_pos, nullptr, 0, st);
+  if (rc) return rc;
+  if (readout) {
+    rc = evavos_bank_write_values(&a.bank, reinterpret_cast<const float*>(d + o_val), (int64_t)CV * n_pos, n_pos, 0,
+                                  n_pos, nullptr, 0, 0, st);
+    if (rc) return rc;
+  }
+  rc = evavos_memread(&a, st);
+  if (rc) return rc;
+  int64_t d2h = 0;
+  if (readout) { EVAVOS_CUDA_OK(cudaMemcpyAsync(readout, d + o_out, b_out, cudaMemcpyDeviceToHost, st)); d2h += b_out; }
+  if (topk_idx) { EVAVOS_CUDA_OK(cudaMemcpyAsync(topk_idx, d + o_idx, b_tk, cudaMemcpyDeviceToHost, st)); d2h += b_tk; }
+  if (topk_weight) { EVAVOS_CUDA_OK(cudaMemcpyAsync(topk_weight, d + o_w, b_tk, cudaMemcpyDeviceToHost, st)); d2h += b_tk; }
+  EVAVOS_CUDA_OK(cudaStreamSynchronize(st));
+  if (h2d_bytes) *h2d_bytes = (int64_t)(b_key + b_q + b_val);
+  if (d2h_bytes) *d2h_bytes = d2h;
+  return EVAVOS_OK;
+}
+
+}  // extern "C"

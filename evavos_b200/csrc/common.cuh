@@ -1,0 +1,110 @@
+// Shared device/host helpers for libevavos_sm100 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/evavos.h"
+
+namespace evavos {
+
+constexpr int kTilePos = EVAVOS_TILE_POS;        // 128 positions per key tile image
+constexpr int kTileKeyBytes = 128 * 128;         // 128 rows x 128 B (64 bf16)
+constexpr int kTileBytes = EVAVOS_TILE_BYTES;    // + 128 fp32 (-|k|^2/2)
+constexpr int kTileSmemStride = 17408;           // tile image padded to a multiple of 1024 B in smem
+constexpr float kEmptyNh = -1.0e30f;             // "-|k|^2/2" of an empty row: can never pass a threshold
+constexpr int kCandCap = 256;                    // candidate slots per query handed to the finalizer
+
+// ---- error plumbing (thread-local message behind evavos_last_error) -------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+#define EVAVOS_CUDA_OK(expr)                                   \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess) return ::evavos::cuda_fail(_e, #expr); \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- order-preserving float <-> uint key ------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t float_to_ordered(float f) {
+  uint32_t u;
+#ifdef __CUDA_ARCH__
+  u = __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c; c.f = f; u = c.u;
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_float(uint32_t k) {
+  uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+
+// Byte offset of (row r, 16-byte chunk c) inside a 128B-swizzled K-major tile (Swizzle<3,4,3>).
+__host__ __device__ __forceinline__ int swizzle128_offset(int r, int c) {
+  return r * 128 + (((c ^ (r & 7)) & 7) << 4);
+}
+
+// Exact fp32 affinity of one (query, key) pair, the arithmetic every selection path agrees on:
+// (-|k|^2 + 2 k.q - |q|^2) / sqrt(CK), accumulated channel by channel with FMAs
+// (prop_net.py:86-90 evaluates the same expression with an SGEMM).
+__device__ __forceinline__ float affinity_from_parts(float kk, float kq, float qq, float inv_sqrt_ck) {
+  float t = -kk + 2.0f * kq;
+  t = t - qq;
+  return t * inv_sqrt_ck;
+}
+
+// ---- launchers implemented in the .cu files -------------------------------------------------
+int launch_write_keys(const EvavosBankShadow& b, const float* src, int64_t src_ch_stride, int64_t pos0,
+                      int64_t n_pos, float* dst_ref, int64_t dst_ref_ch_stride, float* out_pm, void* out_tiles,
+                      float* out_maxnorm, cudaStream_t st);
+int launch_write_values(const EvavosBankShadow& b, const float* src, int64_t src_obj_stride,
+                        int64_t src_ch_stride, int64_t pos0, int64_t n_pos, float* dst_ref,
+                        int64_t dst_ref_obj_stride, int64_t dst_ref_ch_stride, cudaStream_t st);
+
+struct SelectBuffers {
+  float* q_pm;        // [nq_pad][CK]
+  void* q_tiles;      // [MT] tile images
+  float* q_maxnorm;   // scratch scalar
+  float* class_max;   // [G][MT*128][128]
+  float* tau;         // [nq_pad]
+  int32_t* cand_cnt;  // [nq_pad]
+  int32_t* cand;      // [nq_pad][kCandCap]
+  int32_t* work_list; // [nq_pad]
+  int32_t* work_cnt;  // [1]
+};
+
+int launch_brute_select(const float* key_pm, const float* q_pm, int CK, int64_t n_pos, int64_t n_query,
+                        int top_k, const int32_t* work_list, const int32_t* work_cnt, int32_t* cand,
+                        int32_t* cand_cnt, int n_sm, cudaStream_t st);
+int launch_overflow_list(const int32_t* cand_cnt, int64_t n_query, int32_t* work_list, int32_t* work_cnt,
+                         cudaStream_t st);
+int launch_finalize(const float* key_pm, const float* q_pm, int CK, int64_t n_query, int top_k,
+                    const int32_t* cand, const int32_t* cand_cnt, int32_t* out_idx, float* out_weight,
+                    float* out_score, cudaStream_t st);
+int launch_threshold(const float* class_max, int n_chunks, int64_t n_query, int64_t nq_pad, int top_k,
+                     const void* q_tiles, const float* key_maxnorm, float* tau, int32_t* cand_cnt,
+                     cudaStream_t st);
+int launch_score_pass(int pass, const void* q_tiles, const void* key_tiles, int64_t n_pos, int64_t n_query,
+                      int n_chunks, float* class_max, const float* tau, int32_t* cand, int32_t* cand_cnt,
+                      cudaStream_t st);
+int score_pass_chunks(int64_t n_pos, int64_t n_query, int n_sm);
+
+int launch_readout(const EvavosBankShadow& b, const int32_t* idx, const float* weight, int64_t n_query,
+                   int top_k, float* out, int64_t out_obj_stride, int64_t out_ch_stride, cudaStream_t st);
+int launch_affinity_dense(const int32_t* idx, const float* weight, int64_t n_query, int top_k, int64_t n_pos,
+                          float* dense, cudaStream_t st);
+int launch_aggregate(const float* prob, float* out, int K, int64_t npix, int keep_bg, int hard,
+                     cudaStream_t st);
+int launch_topk_merge(const int32_t* cand_idx, const float* cand_score, int64_t n_query, int n_cand, int top_k,
+                      int shard, int n_shards, int64_t pos_per_frame, int32_t* out_idx, float* out_weight,
+                      float* out_score, int32_t* local_idx, cudaStream_t st);
+
+}  // namespace evavos

@@ -1,0 +1,108 @@
+// Merge step of the memory-axis (THW) sharded read (no reference counterpart).
+//
+// After the all-gather every rank holds, per query, n_shards * top_k (score, global position)
+// candidates.  One warp per query selects the global top_k (score descending, position
+// ascending on ties - the same order finalize_kernel uses), computes softmax weights with the
+// GLOBAL maximum and denominator, and maps the winners this shard owns back to local positions
+// so the ordinary sparse readout produces this shard's partial sum.  A sum all-reduce of the
+// partial readouts then equals the single-device readout.
+#include "common.cuh"
+
+namespace evavos {
+
+namespace {
+
+__global__ void __launch_bounds__(128) topk_merge_kernel(
+    const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_score, int64_t n_query, int n_cand,
+    int top_k, int shard, int n_shards, int64_t pos_per_frame, int32_t* __restrict__ out_idx,
+    float* __restrict__ out_weight, float* __restrict__ out_score, int32_t* __restrict__ local_idx) {
+  extern __shared__ unsigned long long smem_keys[];  // [4 warps][n_cand] + [4][EVAVOS_MAX_TOPK]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t q = (int64_t)blockIdx.x * 4 + warp;
+  if (q >= n_query) return;
+  unsigned long long* keys = smem_keys + (size_t)warp * n_cand;
+  unsigned long long* sel = smem_keys + (size_t)4 * n_cand + (size_t)warp * EVAVOS_MAX_TOPK;
+  int live = 0;
+  for (int c = lane; c < n_cand; c += 32) {
+    const int32_t n = cand_idx[q * n_cand + c];
+    unsigned long long k = 0ull;
+    if (n >= 0) {
+      k = ((unsigned long long)float_to_ordered(cand_score[q * n_cand + c]) << 32) |
+          (unsigned long long)(0xffffffffu - (uint32_t)n);
+      ++live;
+    }
+    keys[c] = k;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) live += __shfl_xor_sync(0xffffffffu, live, o);
+  __syncwarp();
+  const int take = min(top_k, live);
+  for (int j = 0; j < take; ++j) {
+    unsigned long long best = 0ull;
+    for (int c = lane; c < n_cand; c += 32) best = keys[c] > best ? keys[c] : best;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    for (int c = lane; c < n_cand; c += 32)
+      if (keys[c] == best) keys[c] = 0ull;  // positions are unique across shards
+    if (lane == 0) sel[j] = best;
+    __syncwarp();
+  }
+  const float s0 = take > 0 ? ordered_to_float((uint32_t)(sel[0] >> 32)) : 0.f;
+  float e[EVAVOS_MAX_TOPK / 32];
+  float part = 0.f;
+#pragma unroll
+  for (int t = 0; t < EVAVOS_MAX_TOPK / 32; ++t) {
+    const int j = lane + 32 * t;
+    e[t] = 0.f;
+    if (j < take) {
+      e[t] = expf(ordered_to_float((uint32_t)(sel[j] >> 32)) - s0);
+      part += e[t];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+#pragma unroll
+  for (int t = 0; t < EVAVOS_MAX_TOPK / 32; ++t) {
+    const int j = lane + 32 * t;
+    if (j >= top_k) continue;
+    const bool ok = j < take;
+    const int64_t o = q * top_k + j;
+    const int64_t pos = ok ? (int64_t)(0xffffffffu - (uint32_t)(sel[j] & 0xffffffffull)) : -1;
+    if (out_idx) out_idx[o] = (int32_t)pos;
+    if (out_weight) out_weight[o] = ok ? e[t] / part : 0.f;
+    if (out_score) out_score[o] = ok ? ordered_to_float((uint32_t)(sel[j] >> 32)) : -INFINITY;
+    if (local_idx) {
+      int32_t loc = -1;
+      if (ok) {
+        const int64_t frame = pos / pos_per_frame, r = pos % pos_per_frame;
+        if (frame % n_shards == shard) loc = (int32_t)((frame / n_shards) * pos_per_frame + r);
+      }
+      local_idx[o] = loc;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_topk_merge(const int32_t* cand_idx, const float* cand_score, int64_t n_query, int n_cand, int top_k,
+                      int shard, int n_shards, int64_t pos_per_frame, int32_t* out_idx, float* out_weight,
+                      float* out_score, int32_t* local_idx, cudaStream_t st) {
+  if (n_query <= 0) return EVAVOS_OK;
+  const size_t smem = sizeof(unsigned long long) * ((size_t)4 * n_cand + 4 * EVAVOS_MAX_TOPK);
+  if (smem > 200 * 1024) {
+    set_error("topk_merge: n_cand=%d too large", n_cand);
+    return EVAVOS_ERR_UNSUPPORTED;
+  }
+  if (smem > 48 * 1024)
+    EVAVOS_CUDA_OK(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  topk_merge_kernel<<<(unsigned)ceil_div(n_query, 4), 128, smem, st>>>(cand_idx, cand_score, n_query, n_cand, top_k,
+                                                                       shard, n_shards, pos_per_frame, out_idx,
+                                                                       out_weight, out_score, local_idx);
+  EVAVOS_CUDA_OK(cudaGetLastError());
+  return EVAVOS_OK;
+}
+
+}  // namespace evavos

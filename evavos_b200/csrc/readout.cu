@@ -1,0 +1,218 @@
+// Sparse value readout and on-demand dense affinity.
+//
+// readout: out[o][c][q] = sum_j w[q][j] * V[o][idx[q][j]][c]   (prop_net.py:108-115 evaluates this
+// as a dense bmm against a matrix with top_k non-zeros per column).  V is the position-major
+// value shadow, so each (query, position) pair is one contiguous CV-row: a warp reads it with
+// 16-byte loads, fully coalesced.  The kernel is L2/HBM-bound: algorithmic bytes
+// = K * CV * min(N, k*HW) * s (every needed row once) + K * CV * HW * 4 (output).
+#include "common.cuh"
+
+namespace evavos {
+
+namespace {
+
+constexpr int kQPerCta = 8;  // one warp per query
+
+__device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
+  a.x = fmaf(w, v.x, a.x);
+  a.y = fmaf(w, v.y, a.y);
+  a.z = fmaf(w, v.z, a.z);
+  a.w = fmaf(w, v.w, a.w);
+}
+
+// fp32 rows, CV = 128 * NV.  grid (ceil(nq/8), K), 256 threads.
+template <int NV>
+__global__ void __launch_bounds__(256) readout_f32_kernel(
+    const float* __restrict__ val_pm, int64_t capacity_pos, const int32_t* __restrict__ idx,
+    const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out,
+    int64_t out_obj_stride, int64_t out_ch_stride) {
+  constexpr int CV = 128 * NV;
+  __shared__ float st[CV][kQPerCta + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int o = blockIdx.y;
+  const int64_t q0 = (int64_t)blockIdx.x * kQPerCta;
+  const int64_t q = q0 + warp;
+  float4 acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (q < n_query) {
+    const float* vbase = val_pm + (int64_t)o * capacity_pos * CV;
+    for (int jb = 0; jb < top_k; jb += 32) {
+      const int jj = jb + lane;
+      const int32_t my_n = jj < top_k ? idx[q * top_k + jj] : -1;
+      const float my_w = jj < top_k ? weight[q * top_k + jj] : 0.f;
+      const int lim = min(32, top_k - jb);
+#pragma unroll 5
+      for (int j = 0; j < lim; ++j) {
+        const int32_t n = __shfl_sync(0xffffffffu, my_n, j);
+        const float w = __shfl_sync(0xffffffffu, my_w, j);
+        if (n < 0) continue;
+        const float4* row = reinterpret_cast<const float4*>(vbase + (int64_t)n * CV) + lane;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) fma4(acc[i], w, __ldg(row + 32 * i));
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 128 + lane * 4;
+    st[c + 0][warp] = acc[i].x;
+    st[c + 1][warp] = acc[i].y;
+    st[c + 2][warp] = acc[i].z;
+    st[c + 3][warp] = acc[i].w;
+  }
+  __syncthreads();
+  const int nq_here = (int)min((int64_t)kQPerCta, n_query - q0);
+  for (int e = threadIdx.x; e < CV * kQPerCta; e += 256) {
+    const int c = e / kQPerCta, w = e % kQPerCta;
+    if (w < nq_here) out[(int64_t)o * out_obj_stride + (int64_t)c * out_ch_stride + q0 + w] = st[c][w];
+  }
+}
+
+// bf16 rows, CV = 256 * NV (8 bf16 per 16-byte load), fp32 accumulation.
+template <int NV>
+__global__ void __launch_bounds__(256) readout_bf16_kernel(
+    const __nv_bfloat16* __restrict__ val_pm, int64_t capacity_pos, const int32_t* __restrict__ idx,
+    const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out,
+    int64_t out_obj_stride, int64_t out_ch_stride) {
+  constexpr int CV = 256 * NV;
+  __shared__ float st[CV][kQPerCta + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int o = blockIdx.y;
+  const int64_t q0 = (int64_t)blockIdx.x * kQPerCta;
+  const int64_t q = q0 + warp;
+  float acc[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+  if (q < n_query) {
+    const __nv_bfloat16* vbase = val_pm + (int64_t)o * capacity_pos * CV;
+    for (int jb = 0; jb < top_k; jb += 32) {
+      const int jj = jb + lane;
+      const int32_t my_n = jj < top_k ? idx[q * top_k + jj] : -1;
+      const float my_w = jj < top_k ? weight[q * top_k + jj] : 0.f;
+      const int lim = min(32, top_k - jb);
+#pragma unroll 5
+      for (int j = 0; j < lim; ++j) {
+        const int32_t n = __shfl_sync(0xffffffffu, my_n, j);
+        const float w = __shfl_sync(0xffffffffu, my_w, j);
+        if (n < 0) continue;
+        const uint4* row = reinterpret_cast<const uint4*>(vbase + (int64_t)n * CV) + lane;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const uint4 u = __ldg(row + 32 * i);
+          const uint32_t ws[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            acc[i][2 * h] = fmaf(w, __uint_as_float(ws[h] << 16), acc[i][2 * h]);
+            acc[i][2 * h + 1] = fmaf(w, __uint_as_float(ws[h] & 0xffff0000u), acc[i][2 * h + 1]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) st[i * 256 + lane * 8 + e][warp] = acc[i][e];
+  __syncthreads();
+  const int nq_here = (int)min((int64_t)kQPerCta, n_query - q0);
+  for (int e = threadIdx.x; e < CV * kQPerCta; e += 256) {
+    const int c = e / kQPerCta, w = e % kQPerCta;
+    if (w < nq_here) out[(int64_t)o * out_obj_stride + (int64_t)c * out_ch_stride + q0 + w] = st[c][w];
+  }
+}
+
+// Any CV / dtype: one CTA per (query, object), threads stride over channels.
+template <typename VT>
+__global__ void __launch_bounds__(128) readout_generic_kernel(
+    const VT* __restrict__ val_pm, int64_t capacity_pos, int CV, const int32_t* __restrict__ idx,
+    const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out,
+    int64_t out_obj_stride, int64_t out_ch_stride) {
+  __shared__ int32_t s_n[EVAVOS_MAX_TOPK];
+  __shared__ float s_w[EVAVOS_MAX_TOPK];
+  const int64_t q = blockIdx.x;
+  const int o = blockIdx.y;
+  for (int j = threadIdx.x; j < top_k; j += blockDim.x) {
+    s_n[j] = idx[q * top_k + j];
+    s_w[j] = weight[q * top_k + j];
+  }
+  __syncthreads();
+  const VT* vbase = val_pm + (int64_t)o * capacity_pos * CV;
+  for (int c = threadIdx.x; c < CV; c += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < top_k; ++j) {
+      const int32_t n = s_n[j];
+      if (n < 0) continue;
+      float v;
+      if constexpr (sizeof(VT) == 2) v = __bfloat162float(vbase[(int64_t)n * CV + c]);
+      else v = vbase[(int64_t)n * CV + c];
+      acc = fmaf(s_w[j], v, acc);
+    }
+    out[(int64_t)o * out_obj_stride + (int64_t)c * out_ch_stride + q] = acc;
+  }
+}
+
+__global__ void scatter_dense_kernel(const int32_t* __restrict__ idx, const float* __restrict__ weight,
+                                     int64_t n_query, int top_k, int64_t n_pos, float* __restrict__ dense) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_query * top_k) return;
+  const int64_t q = e / top_k;
+  const int32_t n = idx[e];
+  if (n >= 0 && n < n_pos) dense[(int64_t)n * n_query + q] = weight[e];
+}
+
+}  // namespace
+
+int launch_readout(const EvavosBankShadow& b, const int32_t* idx, const float* weight, int64_t n_query,
+                   int top_k, float* out, int64_t out_obj_stride, int64_t out_ch_stride, cudaStream_t st) {
+  if (n_query <= 0) return EVAVOS_OK;
+  if (out_ch_stride == 0) out_ch_stride = n_query;
+  if (out_obj_stride == 0) out_obj_stride = (int64_t)b.CV * n_query;
+  const dim3 grid((unsigned)ceil_div(n_query, kQPerCta), (unsigned)b.K);
+  const bool row16 = (reinterpret_cast<uintptr_t>(b.val_pm) % 16) == 0;
+#define EVAVOS_RO_F32(NV)                                                                                  \
+  readout_f32_kernel<NV><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(b.val_pm), b.capacity_pos, idx, \
+                                               weight, n_query, top_k, out, out_obj_stride, out_ch_stride)
+#define EVAVOS_RO_BF16(NV)                                                                                  \
+  readout_bf16_kernel<NV><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(b.val_pm),           \
+                                                b.capacity_pos, idx, weight, n_query, top_k, out,           \
+                                                out_obj_stride, out_ch_stride)
+  if (b.val_dtype == EVAVOS_F32 && row16 && b.CV % 128 == 0 && b.CV <= 512) {
+    switch (b.CV / 128) {
+      case 1: EVAVOS_RO_F32(1); break;
+      case 2: EVAVOS_RO_F32(2); break;
+      case 3: EVAVOS_RO_F32(3); break;
+      default: EVAVOS_RO_F32(4); break;
+    }
+  } else if (b.val_dtype == EVAVOS_BF16 && row16 && b.CV % 256 == 0 && b.CV <= 512) {
+    if (b.CV == 256) EVAVOS_RO_BF16(1);
+    else EVAVOS_RO_BF16(2);
+  } else {
+    const dim3 g2((unsigned)n_query, (unsigned)b.K);
+    if (b.val_dtype == EVAVOS_BF16)
+      readout_generic_kernel<__nv_bfloat16><<<g2, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(b.val_pm),
+                                                                b.capacity_pos, b.CV, idx, weight, n_query, top_k,
+                                                                out, out_obj_stride, out_ch_stride);
+    else
+      readout_generic_kernel<float><<<g2, 128, 0, st>>>(reinterpret_cast<const float*>(b.val_pm), b.capacity_pos,
+                                                        b.CV, idx, weight, n_query, top_k, out, out_obj_stride,
+                                                        out_ch_stride);
+  }
+#undef EVAVOS_RO_F32
+#undef EVAVOS_RO_BF16
+  EVAVOS_CUDA_OK(cudaGetLastError());
+  return EVAVOS_OK;
+}
+
+int launch_affinity_dense(const int32_t* idx, const float* weight, int64_t n_query, int top_k, int64_t n_pos,
+                          float* dense, cudaStream_t st) {
+  EVAVOS_CUDA_OK(cudaMemsetAsync(dense, 0, sizeof(float) * (size_t)n_pos * (size_t)n_query, st));
+  const int64_t total = n_query * top_k;
+  scatter_dense_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(idx, weight, n_query, top_k, n_pos, dense);
+  EVAVOS_CUDA_OK(cudaGetLastError());
+  return EVAVOS_OK;
+}
+
+}  // namespace evavos

@@ -1,0 +1,339 @@
+// tcgen05 / TMEM / TMA candidate filter for the key affinity (sm_100a).
+//
+// S'[q][n] = q^.k^_n - |k_n|^2/2  (bf16 operands, fp32 accumulate in TMEM; the true affinity is
+// (2 S' - |q|^2)/sqrt(CK), a per-query monotone map, prop_net.py:86-90).  The THW x HW matrix
+// never leaves the SM: each 128x128 accumulator tile is consumed out of TMEM by the epilogue
+// warps and only O(k) numbers per query reach HBM.
+//
+//   pass 1: running maximum of S' per (query, column class n mod 128) -> class_max.
+//           The k-th largest of a query's 128 class maxima is a lower bound on its k-th best
+//           score (k distinct positions reach it), found by threshold_kernel.
+//   pass 2: same contraction; every position with S' >= tau_q (bound minus a rigorous bf16
+//           error margin) is appended to the query's candidate list, which therefore
+//           contains the exact fp32 top-k.  finalize_kernel rescoring picks it.
+//
+// Roles per CTA (384 threads, 1 CTA/SM): warp 0 = TMA producer (cp.async.bulk of pre-swizzled
+// 16.5 KB key tile images), warp 1 = MMA issuer (one elected lane, 4 x tcgen05.mma
+// 128x128x16 per tile), warp 2 = TMEM allocator, warps 4-11 = epilogue (two warpgroups, each
+// thread owns one query row and 64 accumulator columns).  Rings: 6 shared-memory key stages,
+// 4 TMEM accumulator stages (4 x 128 columns = all 512).
+#include "common.cuh"
+
+namespace evavos {
+
+namespace {
+
+constexpr int kStages = 6;
+constexpr int kAccStages = 4;
+constexpr int kThreads = 384;
+constexpr int kSmemBytes = kTileSmemStride * (1 + kStages) + 256 + 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, one CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address, 16-byte units
+  d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset between 8-row groups
+  d |= 1ull << 46;                               // descriptor version (Blackwell)
+  d |= 2ull << 61;                               // SWIZZLE_128B
+  return d;
+}
+
+// kind::f16 instruction descriptor: fp32 accumulate, bf16 A and B, both K-major, M=128, N=128.
+constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct PassParams {
+  const uint8_t* q_tiles;
+  const uint8_t* key_tiles;
+  int64_t n_pos;
+  int64_t n_query;
+  int64_t nq_pad;
+  int n_mtiles;
+  int n_ktiles;
+  int n_chunks;
+  float* class_max;
+  const float* tau;
+  int32_t* cand;
+  int32_t* cand_cnt;
+};
+
+template <int PASS>
+__global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t q_smem = base;
+  const uint32_t stage0 = base + kTileSmemStride;
+  const uint32_t bars = base + kTileSmemStride * (1 + kStages);
+  // barrier slots (8 B each)
+  const uint32_t bar_full = bars;                               // [kStages]
+  const uint32_t bar_empty = bars + 8 * kStages;                // [kStages]
+  const uint32_t bar_acc_full = bars + 16 * kStages;            // [kAccStages]
+  const uint32_t bar_acc_empty = bar_acc_full + 8 * kAccStages; // [kAccStages]
+  const uint32_t bar_q = bar_acc_empty + 8 * kAccStages;
+  const uint32_t tmem_slot = bar_q + 8;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + kTileSmemStride * (1 + kStages) + 16 * kStages + 16 * kAccStages + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x % p.n_mtiles;
+  const int chunk = blockIdx.x / p.n_mtiles;
+  const int t0 = (int)(((int64_t)chunk * p.n_ktiles) / p.n_chunks);
+  const int t1 = (int)(((int64_t)(chunk + 1) * p.n_ktiles) / p.n_chunks);
+  const int n_tiles = t1 - t0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 8);
+    }
+    for (int a = 0; a < kAccStages; ++a) {
+      mbar_init(bar_acc_full + 8 * a, 1);
+      mbar_init(bar_acc_empty + 8 * a, 8);
+    }
+    mbar_init(bar_q, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_q, kTileBytes);
+      bulk_g2s(q_smem, p.q_tiles + (int64_t)m_tile * kTileBytes, kTileBytes, bar_q);
+      for (int i = 0; i < n_tiles; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (uint32_t)((i / kStages) & 1);
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        mbar_arrive_expect_tx(bar_full + 8 * s, kTileBytes);
+        bulk_g2s(stage0 + s * kTileSmemStride, p.key_tiles + (int64_t)(t0 + i) * kTileBytes, kTileBytes,
+                 bar_full + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    mbar_wait(bar_q, 0);
+    const uint64_t adesc0 = make_sw128_desc(q_smem);
+    for (int i = 0; i < n_tiles; ++i) {
+      const int s = i % kStages, a = i % kAccStages;
+      mbar_wait(bar_full + 8 * s, (uint32_t)((i / kStages) & 1));
+      mbar_wait(bar_acc_empty + 8 * a, (uint32_t)(((i / kAccStages) & 1) ^ 1));
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t bdesc0 = make_sw128_desc(stage0 + s * kTileSmemStride);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 B): advance 2 x 16-byte units inside the swizzle atom
+          umma_bf16(tmem_base + a * 128, adesc0 + 2 * k, bdesc0 + 2 * k, kInstrDesc, k > 0 ? 1u : 0u);
+        umma_commit(bar_acc_full + 8 * a);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> running class max / candidate append =====
+    const int ew = warp - 4;
+    const int quarter = ew & 3;              // TMEM lane quarter this warp may access
+    const int col0 = (ew >> 2) * 64;         // accumulator columns of this warpgroup
+    const int row = quarter * 32 + lane;
+    const int64_t q = (int64_t)m_tile * 128 + row;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+
+    float cmax[PASS == 1 ? 64 : 1];
+    float thr = INFINITY;
+    if constexpr (PASS == 1) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) cmax[j] = kEmptyNh;
+    } else {
+      if (q < p.n_query) thr = p.tau[q];
+    }
+
+    for (int i = 0; i < n_tiles; ++i) {
+      const int s = i % kStages, a = i % kAccStages;
+      mbar_wait(bar_acc_full + 8 * a, (uint32_t)((i / kAccStages) & 1));
+      mbar_wait(bar_full + 8 * s, (uint32_t)((i / kStages) & 1));  // makes the TMA-written -|k|^2/2 visible
+      tc_fence_after();
+      const int64_t n0 = (int64_t)(t0 + i) * kTilePos;
+      const bool partial = n0 + kTilePos > p.n_pos;
+      const float* nh_s =
+          reinterpret_cast<const float*>(base_ptr + kTileSmemStride * (1 + s) + kTileKeyBytes) + col0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[32];
+        tmem_ld32(lane_addr + (uint32_t)(a * 128 + col0 + h * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 nh = *reinterpret_cast<const float4*>(nh_s + h * 32 + j4 * 4);
+          float s4[4] = {v[j4 * 4 + 0] + nh.x, v[j4 * 4 + 1] + nh.y, v[j4 * 4 + 2] + nh.z, v[j4 * 4 + 3] + nh.w};
+          if (partial) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (n0 + col0 + h * 32 + j4 * 4 + e >= p.n_pos) s4[e] = kEmptyNh;
+          }
+          if constexpr (PASS == 1) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cmax[h * 32 + j4 * 4 + e] = fmaxf(cmax[h * 32 + j4 * 4 + e], s4[e]);
+          } else {
+            const float m4 = fmaxf(fmaxf(s4[0], s4[1]), fmaxf(s4[2], s4[3]));
+            if (m4 >= thr) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (s4[e] >= thr) {
+                  const int pos = atomicAdd(p.cand_cnt + q, 1);
+                  if (pos < kCandCap) p.cand[q * kCandCap + pos] = (int32_t)(n0 + col0 + h * 32 + j4 * 4 + e);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_acc_empty + 8 * a);
+        mbar_arrive(bar_empty + 8 * s);
+      }
+    }
+
+    if constexpr (PASS == 1) {
+      float4* dst = reinterpret_cast<float4*>(p.class_max + ((int64_t)chunk * p.nq_pad + q) * 128 + col0);
+#pragma unroll
+      for (int j4 = 0; j4 < 16; ++j4)
+        dst[j4] = make_float4(cmax[j4 * 4], cmax[j4 * 4 + 1], cmax[j4 * 4 + 2], cmax[j4 * 4 + 3]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+}  // namespace
+
+// Number of memory-axis chunks: CTAs = m_tiles * chunks should fill whole waves of n_sm.
+int score_pass_chunks(int64_t n_pos, int64_t n_query, int n_sm) {
+  const int64_t mt = ceil_div(n_query, 128), nt = ceil_div(n_pos, kTilePos);
+  int64_t g_max = (4 * (int64_t)n_sm) / mt;
+  if (g_max < 1) g_max = 1;
+  if (g_max > nt) g_max = nt;
+  int best = 1;
+  double best_eff = -1.0;
+  for (int64_t g = 1; g <= g_max; ++g) {
+    const int64_t ctas = mt * g;
+    const int64_t waves = ceil_div(ctas, n_sm);
+    double eff = (double)ctas / (double)(waves * n_sm);
+    if (nt / g < 2) eff -= 0.25;  // keep at least two tiles per CTA to amortise the prologue
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = (int)g;
+    }
+  }
+  return best;
+}
+
+int launch_score_pass(int pass, const void* q_tiles, const void* key_tiles, int64_t n_pos, int64_t n_query,
+                      int n_chunks, float* class_max, const float* tau, int32_t* cand, int32_t* cand_cnt,
+                      cudaStream_t st) {
+  PassParams p;
+  p.q_tiles = reinterpret_cast<const uint8_t*>(q_tiles);
+  p.key_tiles = reinterpret_cast<const uint8_t*>(key_tiles);
+  p.n_pos = n_pos;
+  p.n_query = n_query;
+  p.n_mtiles = (int)ceil_div(n_query, 128);
+  p.nq_pad = (int64_t)p.n_mtiles * 128;
+  p.n_ktiles = (int)ceil_div(n_pos, kTilePos);
+  p.n_chunks = n_chunks;
+  p.class_max = class_max;
+  p.tau = tau;
+  p.cand = cand;
+  p.cand_cnt = cand_cnt;
+  const unsigned grid = (unsigned)(p.n_mtiles * n_chunks);
+  static bool attr_set = false;
+  if (!attr_set) {
+    EVAVOS_CUDA_OK(cudaFuncSetAttribute(score_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    EVAVOS_CUDA_OK(cudaFuncSetAttribute(score_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  if (pass == 1)
+    score_pass_kernel<1><<<grid, kThreads, kSmemBytes, st>>>(p);
+  else
+    score_pass_kernel<2><<<grid, kThreads, kSmemBytes, st>>>(p);
+  EVAVOS_CUDA_OK(cudaGetLastError());
+  return EVAVOS_OK;
+}
+
+}  // namespace evavos

@@ -1,0 +1,361 @@
+// Exact fp32 selection kernels on CUDA cores.
+//
+//  brute_select_kernel  exact top-k of one query over ALL memory positions by a 4-round
+//                       8-bit radix select on order-preserving score keys (scores are
+//                       recomputed each round; no N-sized scratch).  It is the whole
+//                       selection in EVAVOS_PATH_SIMT and the overflow path of the tcgen05
+//                       filter (queries whose candidate list exceeded kCandCap, e.g. banks
+//                       with thousands of tied keys).
+//  threshold_kernel     k-th largest of the 128 per-class maxima produced by pass 1 of the
+//                       tcgen05 filter -> per-query admission threshold for pass 2.
+//  finalize_kernel      exact rescoring of <= kCandCap candidates, top-k by (score desc,
+//                       position asc), softmax over the survivors
+//                       (softmax_w_g_top, prop_net.py:53-57).
+//
+// All three agree on one arithmetic for a score: see dot_row / affinity_from_parts.
+#include "common.cuh"
+
+namespace evavos {
+
+namespace {
+
+// kk += |k|^2, kq += k.q over CK channels, channel order 0..CK-1, one FMA per term.
+__device__ __forceinline__ void dot_row(const float4* __restrict__ krow, const float* __restrict__ q, int CK,
+                                        float& kk, float& kq) {
+  kk = 0.f;
+  kq = 0.f;
+  for (int c4 = 0; c4 < (CK >> 2); ++c4) {
+    const float4 kv = __ldg(krow + c4);
+    const float4 qv = *reinterpret_cast<const float4*>(q + 4 * c4);
+    kk = fmaf(kv.x, kv.x, kk); kq = fmaf(kv.x, qv.x, kq);
+    kk = fmaf(kv.y, kv.y, kk); kq = fmaf(kv.y, qv.y, kq);
+    kk = fmaf(kv.z, kv.z, kk); kq = fmaf(kv.z, qv.z, kq);
+    kk = fmaf(kv.w, kv.w, kk); kq = fmaf(kv.w, qv.w, kq);
+  }
+}
+
+__device__ __forceinline__ float sumsq(const float* __restrict__ q, int CK) {
+  float s = 0.f;
+  for (int c = 0; c < CK; ++c) s = fmaf(q[c], q[c], s);
+  return s;
+}
+
+constexpr int kBruteQ = 4;  // queries per CTA pass
+
+// Scores of position n against the kBruteQ queries staged in shared memory.
+__device__ __forceinline__ void score_group(const float* __restrict__ key_pm, int64_t n, int CK,
+                                            const float (*qs)[64], const float* qq, float inv_sqrt_ck,
+                                            float* s) {
+  const float4* krow = reinterpret_cast<const float4*>(key_pm + n * CK);
+  float kk = 0.f, kq[kBruteQ];
+#pragma unroll
+  for (int j = 0; j < kBruteQ; ++j) kq[j] = 0.f;
+  for (int c4 = 0; c4 < (CK >> 2); ++c4) {
+    const float4 kv = __ldg(krow + c4);
+    kk = fmaf(kv.x, kv.x, kk);
+    kk = fmaf(kv.y, kv.y, kk);
+    kk = fmaf(kv.z, kv.z, kk);
+    kk = fmaf(kv.w, kv.w, kk);
+#pragma unroll
+    for (int j = 0; j < kBruteQ; ++j) {
+      const float4 qv = *reinterpret_cast<const float4*>(&qs[j][4 * c4]);
+      kq[j] = fmaf(kv.x, qv.x, kq[j]);
+      kq[j] = fmaf(kv.y, qv.y, kq[j]);
+      kq[j] = fmaf(kv.z, qv.z, kq[j]);
+      kq[j] = fmaf(kv.w, qv.w, kq[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kBruteQ; ++j) s[j] = affinity_from_parts(kk, kq[j], qq[j], inv_sqrt_ck);
+}
+
+__global__ void __launch_bounds__(256) brute_select_kernel(
+    const float* __restrict__ key_pm, const float* __restrict__ q_pm, int CK, int64_t n_pos, int64_t n_query,
+    int top_k, const int32_t* __restrict__ work_list, const int32_t* __restrict__ work_cnt,
+    int32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt) {
+  __shared__ __align__(16) float qs[kBruteQ][64];
+  __shared__ float qq[kBruteQ];
+  __shared__ int qid[kBruteQ];
+  __shared__ unsigned hist[kBruteQ][256];
+  __shared__ uint32_t prefix[kBruteQ];
+  __shared__ int remaining[kBruteQ];
+  __shared__ int gt_cnt[kBruteQ];
+  __shared__ int eq_base[kBruteQ];
+  __shared__ int warp_eq[8][kBruteQ];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n_work = work_cnt ? (int64_t)*work_cnt : n_query;
+  const int64_t groups = (n_work + kBruteQ - 1) / kBruteQ;
+  const float inv_sqrt_ck = 1.0f / sqrtf((float)CK);
+
+  for (int64_t grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    __syncthreads();
+    if (tid < kBruteQ) {
+      const int64_t w = grp * kBruteQ + tid;
+      int q = -1;
+      if (w < n_work) q = work_list ? work_list[w] : (int)w;
+      qid[tid] = q;
+      remaining[tid] = top_k;
+      prefix[tid] = 0;
+      gt_cnt[tid] = 0;
+      eq_base[tid] = 0;
+    }
+    __syncthreads();
+    for (int e = tid; e < kBruteQ * 64; e += 256) {
+      const int j = e >> 6, c = e & 63;
+      const int q = qid[j];
+      qs[j][c] = (q >= 0 && c < CK) ? q_pm[(int64_t)q * CK + c] : 0.f;
+    }
+    __syncthreads();
+    if (tid < kBruteQ) qq[tid] = sumsq(qs[tid], CK);
+    __syncthreads();
+
+    // ---- 4 radix rounds, most significant byte first --------------------------------------
+    for (int round = 0; round < 4; ++round) {
+      const int shift = 24 - 8 * round;
+      for (int e = tid; e < kBruteQ * 256; e += 256) (&hist[0][0])[e] = 0;
+      __syncthreads();
+      uint32_t pfx[kBruteQ];
+#pragma unroll
+      for (int j = 0; j < kBruteQ; ++j) pfx[j] = prefix[j];
+      for (int64_t n = tid; n < n_pos; n += 256) {
+        float s[kBruteQ];
+        score_group(key_pm, n, CK, qs, qq, inv_sqrt_ck, s);
+#pragma unroll
+        for (int j = 0; j < kBruteQ; ++j) {
+          const uint32_t key = float_to_ordered(s[j]);
+          const bool match = (round == 0) || ((key >> (shift + 8)) == pfx[j]);
+          if (match && qid[j] >= 0) atomicAdd(&hist[j][(key >> shift) & 255u], 1u);
+        }
+      }
+      __syncthreads();
+      if (tid < kBruteQ) {
+        const int rem = remaining[tid];
+        int d = 255;
+        int cum = 0;
+        for (; d > 0; --d) {
+          const int c = (int)hist[tid][d];
+          if (cum + c >= rem) break;
+          cum += c;
+        }
+        prefix[tid] = (round == 0 ? 0u : (prefix[tid] << 8)) | (uint32_t)d;
+        remaining[tid] = rem - cum;
+      }
+      __syncthreads();
+    }
+
+    // ---- collect: everything above the k-th key, then the lowest positions among ties ------
+    uint32_t T[kBruteQ];
+    int need[kBruteQ];
+#pragma unroll
+    for (int j = 0; j < kBruteQ; ++j) { T[j] = prefix[j]; need[j] = remaining[j]; }
+    for (int64_t base = 0; base < n_pos; base += 256) {
+      const int64_t n = base + tid;
+      const bool in = n < n_pos;
+      float s[kBruteQ];
+      if (in) score_group(key_pm, n, CK, qs, qq, inv_sqrt_ck, s);
+      bool eq[kBruteQ];
+      int rank[kBruteQ];
+      bool any_eq = false;
+#pragma unroll
+      for (int j = 0; j < kBruteQ; ++j) {
+        const bool live = in && qid[j] >= 0;
+        const uint32_t key = live ? float_to_ordered(s[j]) : 0u;
+        if (live && key > T[j]) {
+          const int pos = atomicAdd(&gt_cnt[j], 1);
+          cand[(int64_t)qid[j] * kCandCap + pos] = (int32_t)n;
+        }
+        eq[j] = live && key == T[j];
+        const unsigned m = __ballot_sync(0xffffffffu, eq[j]);
+        rank[j] = __popc(m & ((1u << lane) - 1u));
+        if (lane == 0) warp_eq[warp][j] = __popc(m);
+        any_eq |= (m != 0u);
+      }
+      if (__syncthreads_or(any_eq)) {
+#pragma unroll
+        for (int j = 0; j < kBruteQ; ++j) {
+          if (eq[j]) {
+            int r = eq_base[j] + rank[j];
+            for (int w = 0; w < warp; ++w) r += warp_eq[w][j];
+            if (r < need[j]) cand[(int64_t)qid[j] * kCandCap + (top_k - need[j]) + r] = (int32_t)n;
+          }
+        }
+        __syncthreads();
+        if (tid < kBruteQ) {
+          int tot = 0;
+          for (int w = 0; w < 8; ++w) tot += warp_eq[w][tid];
+          eq_base[tid] += tot;
+        }
+        __syncthreads();
+      }
+    }
+    if (tid < kBruteQ && qid[tid] >= 0) cand_cnt[qid[tid]] = top_k;
+  }
+}
+
+__global__ void overflow_list_kernel(const int32_t* __restrict__ cand_cnt, int64_t n_query,
+                                     int32_t* __restrict__ work_list, int32_t* __restrict__ work_cnt) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n_query && cand_cnt[q] > kCandCap) {
+    const int pos = atomicAdd(work_cnt, 1);
+    work_list[pos] = (int32_t)q;
+  }
+}
+
+// One warp per query: k-th largest of 128 class maxima by bitwise radix descent.
+__global__ void __launch_bounds__(128) threshold_kernel(
+    const float* __restrict__ class_max, int n_chunks, int64_t n_query, int64_t nq_pad, int top_k,
+    const uint8_t* __restrict__ q_tiles, const float* __restrict__ key_maxnorm, float* __restrict__ tau,
+    int32_t* __restrict__ cand_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (q >= n_query) return;
+  float v[4] = {kEmptyNh, kEmptyNh, kEmptyNh, kEmptyNh};
+  for (int g = 0; g < n_chunks; ++g) {
+    const float* row = class_max + ((int64_t)g * nq_pad + q) * 128;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v[t] = fmaxf(v[t], row[lane + 32 * t]);
+  }
+  uint32_t key[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) key[t] = float_to_ordered(v[t]);
+  uint32_t pfx = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t trial = pfx | (1u << bit);
+    int cnt = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) cnt += __popc(__ballot_sync(0xffffffffu, key[t] >= trial));
+    if (cnt >= top_k) pfx = trial;
+  }
+  if (lane == 0) {
+    const float kth = ordered_to_float(pfx);
+    const float nhq = *reinterpret_cast<const float*>(q_tiles + (q / kTilePos) * (int64_t)kTileBytes +
+                                                      kTileKeyBytes + (q % kTilePos) * 4);
+    const float qn = sqrtf(fmaxf(-2.0f * nhq, 0.f));
+    const float kn = *key_maxnorm;
+    // |q^.k^ - q.k| <= 2^-8 (1 + 2^-10) |q||k| for bf16 round-to-nearest operands, plus slack for the
+    // tensor-core fp32 accumulation and the rounding of -|k|^2/2.
+    const float eps = 0.004f * qn * kn + 2.0e-6f * kn * kn + 1.0e-30f;
+    tau[q] = kth - 2.0f * eps;
+    cand_cnt[q] = 0;
+  }
+}
+
+// One warp per query, 4 warps per CTA.
+__global__ void __launch_bounds__(128) finalize_kernel(
+    const float* __restrict__ key_pm, const float* __restrict__ q_pm, int CK, int64_t n_query, int top_k,
+    const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt, int32_t* __restrict__ out_idx,
+    float* __restrict__ out_weight, float* __restrict__ out_score) {
+  __shared__ __align__(16) float qs_all[4][64];
+  __shared__ unsigned long long sel_all[4][EVAVOS_MAX_TOPK];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t q = (int64_t)blockIdx.x * 4 + warp;
+  if (q >= n_query) return;
+  float* qs = qs_all[warp];
+  unsigned long long* sel = sel_all[warp];
+  for (int c = lane; c < 64; c += 32) qs[c] = (c < CK) ? q_pm[q * CK + c] : 0.f;
+  __syncwarp();
+  const float qq = sumsq(qs, CK);
+  const float inv_sqrt_ck = 1.0f / sqrtf((float)CK);
+  const int cnt = min(cand_cnt[q], kCandCap);
+
+  constexpr int kPerLane = kCandCap / 32;
+  unsigned long long key[kPerLane];
+#pragma unroll
+  for (int t = 0; t < kPerLane; ++t) {
+    const int ci = lane + 32 * t;
+    key[t] = 0ull;
+    if (ci < cnt) {
+      const int32_t n = cand[q * kCandCap + ci];
+      float kk, kq;
+      dot_row(reinterpret_cast<const float4*>(key_pm + (int64_t)n * CK), qs, CK, kk, kq);
+      const float s = affinity_from_parts(kk, kq, qq, inv_sqrt_ck);
+      key[t] = ((unsigned long long)float_to_ordered(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
+    }
+  }
+  const int take = min(top_k, cnt);
+  for (int j = 0; j < take; ++j) {
+    unsigned long long best = key[0];
+#pragma unroll
+    for (int t = 1; t < kPerLane; ++t) best = key[t] > best ? key[t] : best;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+#pragma unroll
+    for (int t = 0; t < kPerLane; ++t)
+      if (key[t] == best) key[t] = 0ull;
+    if (lane == 0) sel[j] = best;
+  }
+  __syncwarp();
+  const float s0 = ordered_to_float((uint32_t)(sel[0] >> 32));
+  float e[EVAVOS_MAX_TOPK / 32];
+  float part = 0.f;
+#pragma unroll
+  for (int t = 0; t < EVAVOS_MAX_TOPK / 32; ++t) {
+    const int j = lane + 32 * t;
+    e[t] = 0.f;
+    if (j < take) {
+      e[t] = expf(ordered_to_float((uint32_t)(sel[j] >> 32)) - s0);  // exp(values - values[:,0])
+      part += e[t];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+#pragma unroll
+  for (int t = 0; t < EVAVOS_MAX_TOPK / 32; ++t) {
+    const int j = lane + 32 * t;
+    if (j < top_k) {
+      const bool live = j < take;
+      const int64_t o = q * top_k + j;
+      if (out_idx) out_idx[o] = live ? (int32_t)(0xffffffffu - (uint32_t)(sel[j] & 0xffffffffull)) : -1;
+      if (out_weight) out_weight[o] = live ? e[t] / part : 0.f;
+      if (out_score) out_score[o] = live ? ordered_to_float((uint32_t)(sel[j] >> 32)) : -INFINITY;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_brute_select(const float* key_pm, const float* q_pm, int CK, int64_t n_pos, int64_t n_query,
+                        int top_k, const int32_t* work_list, const int32_t* work_cnt, int32_t* cand,
+                        int32_t* cand_cnt, int n_sm, cudaStream_t st) {
+  int64_t grid = ceil_div(n_query, kBruteQ);
+  const int64_t cap = (int64_t)n_sm * 8;  // 8 resident 256-thread CTAs per SM
+  if (work_list != nullptr && grid > cap) grid = cap;
+  if (grid > 0x7fffffff) grid = 0x7fffffff;
+  brute_select_kernel<<<(unsigned)grid, 256, 0, st>>>(key_pm, q_pm, CK, n_pos, n_query, top_k, work_list,
+                                                      work_cnt, cand, cand_cnt);
+  EVAVOS_CUDA_OK(cudaGetLastError());
+  return EVAVOS_OK;
+}
+
+int launch_overflow_list(const int32_t* cand_cnt, int64_t n_query, int32_t* work_list, int32_t* work_cnt,
+                         cudaStream_t st) {
+  EVAVOS_CUDA_OK(cudaMemsetAsync(work_cnt, 0, sizeof(int32_t), st));
+  overflow_list_kernel<<<(unsigned)ceil_div(n_query, 256), 256, 0, st>>>(cand_cnt, n_query, work_list, work_cnt);
+  EVAVOS_CUDA_OK(cudaGetLastError());
+  return EVAVOS_OK;
+}
+
+int launch_threshold(const float* class_max, int n_chunks, int64_t n_query, int64_t nq_pad, int top_k,
+                     const void* q_tiles, const float* key_maxnorm, float* tau, int32_t* cand_cnt,
+                     cudaStream_t st) {
+  threshold_kernel<<<(unsigned)ceil_div(n_query, 4), 128, 0, st>>>(
+      class_max, n_chunks, n_query, nq_pad, top_k, reinterpret_cast<const uint8_t*>(q_tiles), key_maxnorm, tau,
+      cand_cnt);
+  EVAVOS_CUDA_OK(cudaGetLastError());
+  return EVAVOS_OK;
+}
+
+int launch_finalize(const float* key_pm, const float* q_pm, int CK, int64_t n_query, int top_k,
+                    const int32_t* cand, const int32_t* cand_cnt, int32_t* out_idx, float* out_weight,
+                    float* out_score, cudaStream_t st) {
+  finalize_kernel<<<(unsigned)ceil_div(n_query, 4), 128, 0, st>>>(key_pm, q_pm, CK, n_query, top_k, cand,
+                                                                  cand_cnt, out_idx, out_weight, out_score);
+  EVAVOS_CUDA_OK(cudaGetLastError());
+  return EVAVOS_OK;
+}
+
+}  // namespace evavos

@@ -1,0 +1,195 @@
+/*
+ * evavos.h - C ABI of libevavos_sm100.so: the B200 (sm_100a) space-time memory read.
+ *
+ * This is the drop-in boundary for the one hot path of EVA-VOS / MiVOS / STCN
+ * (paths below are relative to the reference repository root):
+ *
+ *   evavos_memread          replaces EvalMemoryReader.get_affinity + readout
+ *                           (mivos/model/propagation/prop_net.py:80-115, called from
+ *                           PropagationNetwork.segment_with_query, prop_net.py:179-187)
+ *                           and softmax_w_g_top (prop_net.py:46-72).
+ *   evavos_readout          replaces EvalMemoryReader.readout alone (prop_net.py:108-115).
+ *   evavos_affinity_dense   materialises the dense (N,HW) matrix that get_affinity
+ *                           returns in the reference (prop_net.py:60), on demand only.
+ *   evavos_aggregate_wbg    replaces aggregate_wbg (mivos/model/aggregate.py:22-37).
+ *   evavos_bank_write_keys / evavos_bank_write_values
+ *                           replace the in-place bank append and the certain-memory
+ *                           copy of InferenceCore.do_pass (mivos/inference_core.py:150-155,
+ *                           174-177) and the torch.cat growth in interact (:235-240).
+ *   evavos_topk_merge       the exchange step of the memory-axis sharded read
+ *                           (no reference counterpart).
+ *   evavos_memread_host     the same read with HOST buffers in the reference layout
+ *                           (what a ctypes/cgo caller without device memory would bind).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - all device pointers are owned by the caller (PyTorch's caching allocator in the
+ *     Python host); the library never allocates or frees device memory except inside
+ *     evavos_memread_host, which owns its scratch for the duration of the call.
+ *   - every device entry point is asynchronous and ordered on the cudaStream_t passed
+ *     as `stream` (an opaque pointer here so the header needs no CUDA include).
+ *   - return value: 0 on success, a negative EVAVOS_ERR_* code otherwise; a
+ *     thread-local message is available from evavos_last_error().
+ *   - there is no CPU fallback: on a machine without an sm_100 device the entry
+ *     points return EVAVOS_ERR_CUDA.
+ *
+ * Memory-bank layouts (the API contract, mivos/inference_core.py:150-151)
+ *   keys   (1, CK, T, H, W) fp32     values (K, CV, T, H, W) fp32
+ * described here by (pointer, channel stride, object stride) because do_pass reads
+ * T-slices `[:, :, :m_front]` of a pre-allocated bank (strided views, :167-168).
+ *
+ * Engine-private shadow of a bank ("position-major"), maintained by the two
+ * evavos_bank_write_* calls and consumed by the read:
+ *   key_pm     [n_pos][CK] fp32            exact keys, one 4*CK-byte row per position
+ *   key_tiles  ceil(n_pos/128) tile images of EVAVOS_TILE_BYTES each: 128 bf16 key rows
+ *              in the 128B-swizzled K-major shared-memory layout tcgen05.mma consumes,
+ *              followed by 128 fp32 values -|k|^2/2 (loaded verbatim by one bulk TMA copy)
+ *   key_maxnorm  1 fp32: max |k| over the bank (rigorous bf16 error bound for the filter)
+ *   val_pm     [K][n_pos][CV] fp32 or bf16 value rows
+ */
+#ifndef EVAVOS_H_
+#define EVAVOS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVAVOS_ABI_VERSION 1
+
+#define EVAVOS_OK 0
+#define EVAVOS_ERR_INVALID (-1)     /* bad argument (null pointer, non-positive size, ...) */
+#define EVAVOS_ERR_UNSUPPORTED (-2) /* shape / dtype outside what the kernels implement   */
+#define EVAVOS_ERR_CUDA (-3)        /* a CUDA runtime call or kernel launch failed        */
+#define EVAVOS_ERR_WORKSPACE (-4)   /* caller-provided workspace too small                */
+#define EVAVOS_ERR_TOPK_RANGE (-5)  /* n_pos < top_k: "selected index k out of range" (prop_net.py:53) */
+
+#define EVAVOS_F32 0
+#define EVAVOS_BF16 1
+
+#define EVAVOS_PATH_AUTO 0   /* tcgen05 filter when CK == 64, else SIMT                      */
+#define EVAVOS_PATH_TENSOR 1 /* tcgen05/TMEM candidate filter + exact fp32 rescoring          */
+#define EVAVOS_PATH_SIMT 2   /* exact fp32 CUDA-core radix select (also the overflow path)    */
+
+#define EVAVOS_TILE_POS 128      /* memory positions per key tile image  */
+#define EVAVOS_TILE_BYTES 16896  /* 128 rows x 128 B (bf16, CK=64) + 128 x 4 B               */
+#define EVAVOS_MAX_TOPK 128
+
+typedef void* evavos_stream_t; /* cudaStream_t */
+
+/* Engine-private shadow of a memory bank (all device pointers). */
+typedef struct EvavosBankShadow {
+  float* key_pm;       /* [capacity_pos][CK] fp32                                   */
+  void* key_tiles;     /* ceil(capacity_pos/128) * EVAVOS_TILE_BYTES, 1024B aligned; NULL when CK != 64 */
+  float* key_maxnorm;  /* 1 fp32, must be zero-initialised by the caller             */
+  void* val_pm;        /* [K][capacity_pos][CV] of val_dtype                         */
+  int64_t capacity_pos; /* positions the buffers were sized for                      */
+  int32_t K;
+  int32_t CK;
+  int32_t CV;
+  int32_t val_dtype;   /* EVAVOS_F32 | EVAVOS_BF16                                   */
+} EvavosBankShadow;
+
+/* Arguments of the fused read. */
+typedef struct EvavosMemReadArgs {
+  EvavosBankShadow bank;
+  const float* query;      /* (CK, n_query) fp32, row stride query_ch_stride; n_query = HW * frames */
+  float* readout;          /* (K, CV, n_query) fp32 or NULL to skip the readout       */
+  int32_t* topk_idx;       /* (n_query, top_k) memory positions, best first; or NULL  */
+  float* topk_weight;      /* (n_query, top_k) softmax weights; or NULL               */
+  float* topk_score;       /* (n_query, top_k) affinities (-a+b-c)/sqrt(CK); or NULL  */
+  void* workspace;
+  int64_t workspace_bytes;
+  int64_t n_pos;           /* N = m_front * H * W positions to read (<= capacity_pos) */
+  int64_t n_query;
+  int64_t query_ch_stride;
+  int64_t readout_obj_stride; /* elements between objects in `readout` (0 -> CV*n_query) */
+  int64_t readout_ch_stride;  /* elements between channels in `readout` (0 -> n_query)    */
+  int32_t top_k;
+  int32_t path;            /* EVAVOS_PATH_*                                           */
+  int32_t n_sm;            /* SM count to size grids for (0 -> query the device)      */
+  int32_t reserved;
+} EvavosMemReadArgs;
+
+int evavos_abi_version(void);
+const char* evavos_last_error(void);
+size_t evavos_sizeof_bank_shadow(void);
+size_t evavos_sizeof_memread_args(void);
+
+/* Bytes of key_tiles needed for `capacity_pos` positions. */
+size_t evavos_key_tiles_bytes(int64_t capacity_pos);
+
+/*
+ * Write `n_pos` key positions starting at bank position `pos0`.
+ *   src: (CK, n_pos) fp32 with row stride src_ch_stride (a new frame k16 of
+ *        inference_core.py:175, or a T-slice of an existing bank).
+ *   dst_ref: optional reference-layout bank keys (1,CK,T,H,W); element
+ *        [c*dst_ref_ch_stride + pos0 + i] receives src[c][i].  NULL to skip.
+ * Updates key_pm, key_tiles (if non-NULL) and key_maxnorm of `bank`.
+ * When the written range ends inside a tile, the tile's remaining rows are marked empty.
+ */
+int evavos_bank_write_keys(const EvavosBankShadow* bank, const float* src, int64_t src_ch_stride,
+                           int64_t pos0, int64_t n_pos, float* dst_ref, int64_t dst_ref_ch_stride,
+                           evavos_stream_t stream);
+
+/*
+ * Write `n_pos` value positions starting at `pos0` for all K objects.
+ *   src: (K, CV, n_pos) fp32, strides src_obj_stride / src_ch_stride (inference_core.py:176).
+ *   dst_ref: optional reference-layout bank values (K,CV,T,H,W).
+ */
+int evavos_bank_write_values(const EvavosBankShadow* bank, const float* src, int64_t src_obj_stride,
+                             int64_t src_ch_stride, int64_t pos0, int64_t n_pos, float* dst_ref,
+                             int64_t dst_ref_obj_stride, int64_t dst_ref_ch_stride, evavos_stream_t stream);
+
+size_t evavos_memread_workspace_bytes(const EvavosMemReadArgs* args);
+int evavos_memread(const EvavosMemReadArgs* args, evavos_stream_t stream);
+
+/* Sparse readout: out[o][c][q] = sum_j weight[q][j] * val_pm[o][idx[q][j]][c]; idx < 0 entries are skipped. */
+int evavos_readout(const EvavosBankShadow* bank, const int32_t* idx, const float* weight, int64_t n_query,
+                   int32_t top_k, float* out, int64_t out_obj_stride, int64_t out_ch_stride,
+                   evavos_stream_t stream);
+
+/* dense[n][q] = weight of position n for query q, zeros elsewhere: (n_pos, n_query) fp32 (prop_net.py:60). */
+int evavos_affinity_dense(const int32_t* idx, const float* weight, int64_t n_query, int32_t top_k,
+                          int64_t n_pos, float* dense, evavos_stream_t stream);
+
+/* Soft aggregation: prob (K, npix) fp32 -> out (K+1, npix) if keep_bg else (K, npix). */
+int evavos_aggregate_wbg(const float* prob, float* out, int32_t K, int64_t npix, int32_t keep_bg,
+                         int32_t hard, evavos_stream_t stream);
+
+/*
+ * Merge step of the memory-axis sharded read.  cand_idx/cand_score: (n_query, n_cand)
+ * all-gathered per-shard top-k (GLOBAL positions, -1 = empty).  Selects the global top_k
+ * per query (score descending, position ascending on ties), computes softmax weights with
+ * the global max and denominator, and emits
+ *   out_idx/out_weight/out_score (n_query, top_k): the merged result (any may be NULL)
+ *   local_idx (n_query, top_k): LOCAL position of winners owned by this shard, -1 otherwise,
+ *     where a global position p = frame*pos_per_frame + r is owned iff frame % n_shards == shard
+ *     and its local position is (frame / n_shards)*pos_per_frame + r.
+ */
+int evavos_topk_merge(const int32_t* cand_idx, const float* cand_score, int64_t n_query, int32_t n_cand,
+                      int32_t top_k, int32_t shard, int32_t n_shards, int64_t pos_per_frame,
+                      int32_t* out_idx, float* out_weight, float* out_score, int32_t* local_idx,
+                      evavos_stream_t stream);
+
+/*
+ * Host-buffer form of the read, reference layouts, synchronous:
+ *   mem_key (CK, n_pos) fp32 contiguous, query (CK, n_query), mem_value (K, CV, n_pos),
+ *   readout (K, CV, n_query); topk_idx/topk_weight optional (n_query, top_k).
+ * Copies the inputs to the device, builds the shadow, reads, copies the result back.
+ * h2d_bytes/d2h_bytes (optional) receive the bytes moved.
+ */
+int evavos_memread_host(const float* mem_key, const float* query, const float* mem_value, int32_t K,
+                        int32_t CK, int32_t CV, int64_t n_pos, int64_t n_query, int32_t top_k, int32_t path,
+                        float* readout, int32_t* topk_idx, float* topk_weight, int64_t* h2d_bytes,
+                        int64_t* d2h_bytes);
+
+/* Frees the device scratch evavos_memread_host keeps between calls. */
+int evavos_release_host_scratch(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVAVOS_H_ */
