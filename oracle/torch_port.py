@@ -41,7 +41,8 @@ def dense_readout(affinity: torch.Tensor, mem_value: torch.Tensor) -> torch.Tens
     """(1,CV,T,H,W) x (1,N,HW) -> (1,CV,H,W); prop_net.py:108-115 (bmm over a strided view)."""
     b, cv, t, h, w = mem_value.shape
     out = torch.bmm(mem_value.view(b, cv, t * h * w), affinity)
-    return out.view(b, cv, h, w)
+    # (bench.py times a slice of the query columns when the full frame is too slow: keep it flat then)
+    return out.view(b, cv, h, w) if out.shape[-1] == h * w else out
 
 
 def memory_read(mem_key, query_key, mem_value, top_k: int = 50) -> torch.Tensor:
