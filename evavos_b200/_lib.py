@@ -14,7 +14,7 @@ ABI_VERSION = 1
 F32, BF16 = 0, 1
 PATH_AUTO, PATH_TENSOR, PATH_SIMT = 0, 1, 2
 TILE_POS = 128
-TILE_BYTES = 16896
+TILE_BYTES = 20480
 MAX_TOPK = 128
 ERR_TOPK_RANGE = -5
 

@@ -66,15 +66,10 @@ Carve carve_workspace(const EvavosMemReadArgs& a, int n_chunks, uint8_t* base) {
     off += align_up(bytes, 1024);
     return p;
   };
-  c.sb.q_pm = reinterpret_cast<float*>(take(sizeof(float) * nq_pad * a.bank.CK));
-  c.sb.q_tiles = take((size_t)mt * kTileBytes);
-  c.sb.q_maxnorm = reinterpret_cast<float*>(take(sizeof(float)));
   c.sb.class_max = reinterpret_cast<float*>(take(n_chunks > 0 ? sizeof(float) * (size_t)n_chunks * nq_pad * 128 : 0));
   c.sb.tau = reinterpret_cast<float*>(take(sizeof(float) * nq_pad));
   c.sb.cand_cnt = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * nq_pad));
   c.sb.cand = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * nq_pad * kCandCap));
-  c.sb.work_list = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * nq_pad));
-  c.sb.work_cnt = reinterpret_cast<int32_t*>(take(sizeof(int32_t)));
   c.idx = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * a.n_query * a.top_k));
   c.weight = reinterpret_cast<float*>(take(sizeof(float) * a.n_query * a.top_k));
   c.total = off + 1024;  // slack for aligning the caller's pointer
@@ -150,9 +145,7 @@ int evavos_bank_write_keys(const EvavosBankShadow* bank, const float* src, int64
               (long long)bank->capacity_pos);
     return EVAVOS_ERR_INVALID;
   }
-  void* tiles = (bank->CK == 64) ? bank->key_tiles : nullptr;
-  return launch_write_keys(*bank, src, src_ch_stride, pos0, n_pos, dst_ref, dst_ref_ch_stride, bank->key_pm, tiles,
-                           bank->key_maxnorm, (cudaStream_t)stream);
+  return launch_write_keys(*bank, src, src_ch_stride, pos0, n_pos, dst_ref, dst_ref_ch_stride, (cudaStream_t)stream);
 }
 
 int evavos_bank_write_values(const EvavosBankShadow* bank, const float* src, int64_t src_obj_stride,
@@ -197,43 +190,37 @@ int evavos_memread(const EvavosMemReadArgs* a, evavos_stream_t stream) {
   const Carve c = carve_workspace(*a, chunks, base);
   const int CK = a->bank.CK;
 
-  // 1. query shadow: position-major fp32 rows (+ bf16 tile images, -|q|^2/2)
-  EvavosBankShadow qb = a->bank;
-  qb.capacity_pos = ceil_div(a->n_query, 128) * 128;
-  rc = launch_write_keys(qb, a->query, a->query_ch_stride, 0, a->n_query, nullptr, 0, c.sb.q_pm,
-                         tensor ? c.sb.q_tiles : nullptr, nullptr, st);
-  if (rc) return rc;
+  const int64_t nq_pad = ceil_div(a->n_query, 128) * 128;
 
-  // 2. candidate generation
+  // 1. candidate generation (the query is consumed in the caller's layout; no query shadow)
   if (tensor) {
-    rc = launch_score_pass(1, c.sb.q_tiles, a->bank.key_tiles, a->n_pos, a->n_query, chunks, c.sb.class_max, nullptr,
-                           nullptr, nullptr, st);
+    rc = launch_score_pass(1, a->query, a->query_ch_stride, a->bank.key_tiles, a->n_pos, a->n_query, chunks,
+                           c.sb.class_max, nullptr, nullptr, nullptr, st);
     if (rc) return rc;
-    rc = launch_threshold(c.sb.class_max, chunks, a->n_query, qb.capacity_pos, a->top_k, c.sb.q_tiles,
+    rc = launch_threshold(c.sb.class_max, chunks, a->n_query, nq_pad, a->top_k, a->query, a->query_ch_stride,
                           a->bank.key_maxnorm, c.sb.tau, c.sb.cand_cnt, st);
     if (rc) return rc;
-    rc = launch_score_pass(2, c.sb.q_tiles, a->bank.key_tiles, a->n_pos, a->n_query, chunks, nullptr, c.sb.tau,
-                           c.sb.cand, c.sb.cand_cnt, st);
+    rc = launch_score_pass(2, a->query, a->query_ch_stride, a->bank.key_tiles, a->n_pos, a->n_query, chunks, nullptr,
+                           c.sb.tau, c.sb.cand, c.sb.cand_cnt, st);
     if (rc) return rc;
-    rc = launch_overflow_list(c.sb.cand_cnt, a->n_query, c.sb.work_list, c.sb.work_cnt, st);
-    if (rc) return rc;
-    rc = launch_brute_select(a->bank.key_pm, c.sb.q_pm, CK, a->n_pos, a->n_query, a->top_k, c.sb.work_list,
-                             c.sb.work_cnt, c.sb.cand, c.sb.cand_cnt, n_sm, st);
+    // queries whose candidate list overflowed (massive ties) are redone exactly
+    rc = launch_brute_select(a->bank.key_pm, a->query, a->query_ch_stride, CK, a->n_pos, a->n_query, a->top_k, 1,
+                             c.sb.cand, c.sb.cand_cnt, n_sm, st);
     if (rc) return rc;
   } else {
-    rc = launch_brute_select(a->bank.key_pm, c.sb.q_pm, CK, a->n_pos, a->n_query, a->top_k, nullptr, nullptr,
+    rc = launch_brute_select(a->bank.key_pm, a->query, a->query_ch_stride, CK, a->n_pos, a->n_query, a->top_k, 0,
                              c.sb.cand, c.sb.cand_cnt, n_sm, st);
     if (rc) return rc;
   }
 
-  // 3. exact rescoring, top-k, softmax
+  // 2. exact rescoring, top-k, softmax
   int32_t* idx = a->topk_idx ? a->topk_idx : c.idx;
   float* weight = a->topk_weight ? a->topk_weight : c.weight;
-  rc = launch_finalize(a->bank.key_pm, c.sb.q_pm, CK, a->n_query, a->top_k, c.sb.cand, c.sb.cand_cnt, idx, weight,
-                       a->topk_score, st);
+  rc = launch_finalize(a->bank.key_pm, a->query, a->query_ch_stride, CK, a->n_query, a->top_k, c.sb.cand,
+                       c.sb.cand_cnt, idx, weight, a->topk_score, st);
   if (rc) return rc;
 
-  // 4. sparse readout for all objects
+  // 3. sparse readout for all objects
   if (a->readout) {
     rc = launch_readout(a->bank, idx, weight, a->n_query, a->top_k, a->readout, a->readout_obj_stride,
                         a->readout_ch_stride, st);

@@ -5,7 +5,7 @@
 // torch.cat growth in interact (:235-240).  One pass over the new frame writes
 //   - the reference-layout bank (1,CK,T,H,W)/(K,CV,T,H,W) (optional),
 //   - key_pm  [pos][CK] fp32 rows for exact rescoring,
-//   - key tile images (bf16, 128B-swizzled K-major + -|k|^2/2) for tcgen05.mma,
+//   - key tile images (bf16, 128B-swizzled K-major + a bf16-split -|k|^2/2 K slice) for tcgen05.mma,
 //   - val_pm  [K][pos][CV] rows for the coalesced sparse readout.
 // Both kernels are HBM-bound transposes: algorithmic bytes = 2 * (CK + K*CV) * n_pos * 4
 // (read once, write reference layout + shadow).
@@ -16,6 +16,21 @@ namespace evavos {
 namespace {
 
 constexpr int kKeyBlockPos = 64;
+
+// (hi, mid, lo, 0, 0, 0, 0, 0) bf16: hi + mid + lo == x to 24 bits.
+__device__ __forceinline__ uint4 nh_slice(float x) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(hi);
+  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(mid);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(r2);
+  uint4 w;
+  w.x = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16);
+  w.y = (uint32_t)__bfloat16_as_ushort(lo);
+  w.z = 0;
+  w.w = 0;
+  return w;
+}
 
 // 256 threads, 64 positions per CTA, 4 threads per position.
 __global__ void __launch_bounds__(256) write_keys_kernel(
@@ -70,7 +85,12 @@ __global__ void __launch_bounds__(256) write_keys_kernel(
       }
       *reinterpret_cast<uint4*>(tb + swizzle128_offset(r, chunk)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    if (part == 0) *reinterpret_cast<float*>(tb + kTileKeyBytes + r * 4) = -0.5f * ss;
+    if (part < 2) {
+      // extra K slice: -|k|^2/2 split into three bf16 terms (24 mantissa bits), then zeros
+      uint4 aug = make_uint4(0, 0, 0, 0);
+      if (part == 0) aug = nh_slice(-0.5f * ss);
+      *reinterpret_cast<uint4*>(tb + kTileKeyBytes + swizzle32_offset(r, part)) = aug;
+    }
   }
 
   // Rows between the end of the written range and the end of its tile become empty rows.
@@ -82,7 +102,9 @@ __global__ void __launch_bounds__(256) write_keys_kernel(
       for (int e = tid; e < (kTilePos - r_end) * 8; e += 256) {
         const int r = r_end + e / 8, chunk = e % 8;
         *reinterpret_cast<uint4*>(tb + swizzle128_offset(r, chunk)) = make_uint4(0, 0, 0, 0);
-        if (chunk == 0) *reinterpret_cast<float*>(tb + kTileKeyBytes + r * 4) = kEmptyNh;
+        if (chunk < 2)
+          *reinterpret_cast<uint4*>(tb + kTileKeyBytes + swizzle32_offset(r, chunk)) =
+              chunk == 0 ? nh_slice(kEmptyNh) : make_uint4(0, 0, 0, 0);
       }
     }
   }
@@ -140,12 +162,12 @@ __global__ void __launch_bounds__(256) write_values_kernel(
 }  // namespace
 
 int launch_write_keys(const EvavosBankShadow& b, const float* src, int64_t src_ch_stride, int64_t pos0,
-                      int64_t n_pos, float* dst_ref, int64_t dst_ref_ch_stride, float* out_pm, void* out_tiles,
-                      float* out_maxnorm, cudaStream_t st) {
+                      int64_t n_pos, float* dst_ref, int64_t dst_ref_ch_stride, cudaStream_t st) {
   if (n_pos <= 0) return EVAVOS_OK;
   const int grid = (int)ceil_div(n_pos, kKeyBlockPos);
+  uint8_t* tiles = (b.CK == 64) ? reinterpret_cast<uint8_t*>(b.key_tiles) : nullptr;
   write_keys_kernel<<<grid, 256, 0, st>>>(src, src_ch_stride, pos0, n_pos, b.CK, dst_ref, dst_ref_ch_stride,
-                                          out_pm, reinterpret_cast<uint8_t*>(out_tiles), out_maxnorm);
+                                          b.key_pm, tiles, b.key_maxnorm);
   EVAVOS_CUDA_OK(cudaGetLastError());
   return EVAVOS_OK;
 }

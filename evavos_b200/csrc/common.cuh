@@ -12,8 +12,7 @@ namespace evavos {
 
 constexpr int kTilePos = EVAVOS_TILE_POS;        // 128 positions per key tile image
 constexpr int kTileKeyBytes = 128 * 128;         // 128 rows x 128 B (64 bf16)
-constexpr int kTileBytes = EVAVOS_TILE_BYTES;    // + 128 fp32 (-|k|^2/2)
-constexpr int kTileSmemStride = 17408;           // tile image padded to a multiple of 1024 B in smem
+constexpr int kTileBytes = EVAVOS_TILE_BYTES;    // + 128 rows x 32 B: bf16 (hi, mid, lo) split of -|k|^2/2, zero padded
 constexpr float kEmptyNh = -1.0e30f;             // "-|k|^2/2" of an empty row: can never pass a threshold
 constexpr int kCandCap = 256;                    // candidate slots per query handed to the finalizer
 
@@ -52,6 +51,11 @@ __host__ __device__ __forceinline__ int swizzle128_offset(int r, int c) {
   return r * 128 + (((c ^ (r & 7)) & 7) << 4);
 }
 
+// Byte offset of (row r, 16-byte chunk c in {0,1}) inside a 32B-swizzled K-major tile (Swizzle<1,4,3>).
+__host__ __device__ __forceinline__ int swizzle32_offset(int r, int c) {
+  return r * 32 + (((c ^ (r >> 2)) & 1) << 4);
+}
+
 // Exact fp32 affinity of one (query, key) pair, the arithmetic every selection path agrees on:
 // (-|k|^2 + 2 k.q - |q|^2) / sqrt(CK), accumulated channel by channel with FMAs
 // (prop_net.py:86-90 evaluates the same expression with an SGEMM).
@@ -63,38 +67,32 @@ __device__ __forceinline__ float affinity_from_parts(float kk, float kq, float q
 
 // ---- launchers implemented in the .cu files -------------------------------------------------
 int launch_write_keys(const EvavosBankShadow& b, const float* src, int64_t src_ch_stride, int64_t pos0,
-                      int64_t n_pos, float* dst_ref, int64_t dst_ref_ch_stride, float* out_pm, void* out_tiles,
-                      float* out_maxnorm, cudaStream_t st);
+                      int64_t n_pos, float* dst_ref, int64_t dst_ref_ch_stride, cudaStream_t st);
 int launch_write_values(const EvavosBankShadow& b, const float* src, int64_t src_obj_stride,
                         int64_t src_ch_stride, int64_t pos0, int64_t n_pos, float* dst_ref,
                         int64_t dst_ref_obj_stride, int64_t dst_ref_ch_stride, cudaStream_t st);
 
 struct SelectBuffers {
-  float* q_pm;        // [nq_pad][CK]
-  void* q_tiles;      // [MT] tile images
-  float* q_maxnorm;   // scratch scalar
   float* class_max;   // [G][MT*128][128]
   float* tau;         // [nq_pad]
   int32_t* cand_cnt;  // [nq_pad]
   int32_t* cand;      // [nq_pad][kCandCap]
-  int32_t* work_list; // [nq_pad]
-  int32_t* work_cnt;  // [1]
 };
 
-int launch_brute_select(const float* key_pm, const float* q_pm, int CK, int64_t n_pos, int64_t n_query,
-                        int top_k, const int32_t* work_list, const int32_t* work_cnt, int32_t* cand,
-                        int32_t* cand_cnt, int n_sm, cudaStream_t st);
-int launch_overflow_list(const int32_t* cand_cnt, int64_t n_query, int32_t* work_list, int32_t* work_cnt,
-                         cudaStream_t st);
-int launch_finalize(const float* key_pm, const float* q_pm, int CK, int64_t n_query, int top_k,
-                    const int32_t* cand, const int32_t* cand_cnt, int32_t* out_idx, float* out_weight,
+// The query is always addressed in the caller's layout: element (c, q) at query[c * query_ch_stride + q].
+// only_overflow != 0: process only queries whose candidate count exceeded kCandCap (tcgen05 filter overflow).
+int launch_brute_select(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_pos,
+                        int64_t n_query, int top_k, int only_overflow, int32_t* cand, int32_t* cand_cnt, int n_sm,
+                        cudaStream_t st);
+int launch_finalize(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_query,
+                    int top_k, const int32_t* cand, const int32_t* cand_cnt, int32_t* out_idx, float* out_weight,
                     float* out_score, cudaStream_t st);
 int launch_threshold(const float* class_max, int n_chunks, int64_t n_query, int64_t nq_pad, int top_k,
-                     const void* q_tiles, const float* key_maxnorm, float* tau, int32_t* cand_cnt,
-                     cudaStream_t st);
-int launch_score_pass(int pass, const void* q_tiles, const void* key_tiles, int64_t n_pos, int64_t n_query,
-                      int n_chunks, float* class_max, const float* tau, int32_t* cand, int32_t* cand_cnt,
-                      cudaStream_t st);
+                     const float* query, int64_t query_ch_stride, const float* key_maxnorm, float* tau,
+                     int32_t* cand_cnt, cudaStream_t st);
+int launch_score_pass(int pass, const float* query, int64_t query_ch_stride, const void* key_tiles, int64_t n_pos,
+                      int64_t n_query, int n_chunks, float* class_max, const float* tau, int32_t* cand,
+                      int32_t* cand_cnt, cudaStream_t st);
 int score_pass_chunks(int64_t n_pos, int64_t n_query, int n_sm);
 
 int launch_readout(const EvavosBankShadow& b, const int32_t* idx, const float* weight, int64_t n_query,

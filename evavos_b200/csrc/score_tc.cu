@@ -1,22 +1,26 @@
 // tcgen05 / TMEM / TMA candidate filter for the key affinity (sm_100a).
 //
 // S'[q][n] = q^.k^_n - |k_n|^2/2  (bf16 operands, fp32 accumulate in TMEM; the true affinity is
-// (2 S' - |q|^2)/sqrt(CK), a per-query monotone map, prop_net.py:86-90).  The THW x HW matrix
-// never leaves the SM: each 128x128 accumulator tile is consumed out of TMEM by the epilogue
-// warps and only O(k) numbers per query reach HBM.
+// (2 S' - |q|^2)/sqrt(CK), a per-query monotone map, prop_net.py:86-90).  The -|k|^2/2 term is
+// part of the contraction: every key row carries a 16-wide extra K slice (hi, mid, lo bf16 split
+// of -|k|^2/2, zeros) that meets (1, 1, 1, 0...) on the query side, so the accumulator tile IS the
+// score tile and the epilogue spends one instruction per score.  The THW x HW matrix never leaves
+// the SM: each 128x128 accumulator tile is consumed out of TMEM and only O(k) numbers per query
+// reach HBM.
 //
 //   pass 1: running maximum of S' per (query, column class n mod 128) -> class_max.
 //           The k-th largest of a query's 128 class maxima is a lower bound on its k-th best
-//           score (k distinct positions reach it), found by threshold_kernel.
+//           score (k distinct positions reach it); threshold_kernel finds it.
 //   pass 2: same contraction; every position with S' >= tau_q (bound minus a rigorous bf16
 //           error margin) is appended to the query's candidate list, which therefore
-//           contains the exact fp32 top-k.  finalize_kernel rescoring picks it.
+//           contains the exact fp32 top-k.  finalize_kernel's exact rescoring picks it.
 //
-// Roles per CTA (384 threads, 1 CTA/SM): warp 0 = TMA producer (cp.async.bulk of pre-swizzled
-// 16.5 KB key tile images), warp 1 = MMA issuer (one elected lane, 4 x tcgen05.mma
-// 128x128x16 per tile), warp 2 = TMEM allocator, warps 4-11 = epilogue (two warpgroups, each
-// thread owns one query row and 64 accumulator columns).  Rings: 6 shared-memory key stages,
-// 4 TMEM accumulator stages (4 x 128 columns = all 512).
+// Roles per CTA (384 threads, 1 CTA/SM, one wave): warp 0 = TMA producer (cp.async.bulk of
+// pre-swizzled 20 KB key tile images), warp 1 = MMA issuer (one elected lane, 5 x tcgen05.mma
+// 128x128x16 per tile), warp 2 = TMEM allocator, warps 4-11 = epilogue (two warpgroups, each thread
+// owns one query row and 64 accumulator columns).  Rings: 6 shared-memory key stages, 4 TMEM
+// accumulator stages (4 x 128 columns = all 512).  The query tile is converted to bf16 and
+// swizzled into shared memory by the CTA itself.
 #include "common.cuh"
 
 namespace evavos {
@@ -26,7 +30,10 @@ namespace {
 constexpr int kStages = 6;
 constexpr int kAccStages = 4;
 constexpr int kThreads = 384;
-constexpr int kSmemBytes = kTileSmemStride * (1 + kStages) + 256 + 1024;
+constexpr int kEpiThreads = 256;
+constexpr int kPend = 8;  // private candidate slots per epilogue thread before a flush
+constexpr int kBarBytes = 256;
+constexpr int kSmemBytes = kTileBytes * (1 + kStages) + kBarBytes + (kPend + 1) * kEpiThreads * 4 + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -77,15 +84,18 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart).
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+// K-major operand descriptors (16-byte units; version 1 = Blackwell).
+//   SWIZZLE_128B: rows of 64 bf16 = 128 B, 8-row groups 1024 B apart.
+//   SWIZZLE_32B : rows of 16 bf16 =  32 B, 8-row groups  256 B apart (the -|k|^2/2 slice).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint64_t layout) {
   uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address, 16-byte units
-  d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset between 8-row groups
-  d |= 1ull << 46;                               // descriptor version (Blackwell)
-  d |= 2ull << 61;                               // SWIZZLE_128B
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= 1ull << 46;
+  d |= layout << 61;
   return d;
 }
+constexpr uint64_t kLayoutSw128 = 2, kLayoutSw32 = 6;
 
 // kind::f16 instruction descriptor: fp32 accumulate, bf16 A and B, both K-major, M=128, N=128.
 constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
@@ -106,7 +116,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct PassParams {
-  const uint8_t* q_tiles;
+  const float* query;       // (64, n_query) fp32, row stride query_ch_stride
+  int64_t query_ch_stride;
   const uint8_t* key_tiles;
   int64_t n_pos;
   int64_t n_query;
@@ -120,6 +131,54 @@ struct PassParams {
   int32_t* cand_cnt;
 };
 
+// Candidate append of pass 2: private shared-memory slots (slot e of a thread at slots[e * kEpiThreads],
+// its fill count at slots[kPend * kEpiThreads]), one global atomic per kPend hits.  Kept out of line:
+// hits are rare (about top_k + margin per query over the whole bank) and the hot loop stays small.
+__device__ __noinline__ void flush_pending(int32_t* slots, int32_t* cand, int32_t* cand_cnt, int64_t q) {
+  const int n = slots[kPend * kEpiThreads];
+  if (n == 0) return;
+  const int base = atomicAdd(cand_cnt + q, n);
+  for (int e = 0; e < n; ++e)
+    if (base + e < kCandCap) cand[q * kCandCap + base + e] = slots[e * kEpiThreads];
+  slots[kPend * kEpiThreads] = 0;
+}
+__device__ __noinline__ void hit4(float s0, float s1, float s2, float s3, float thr, int32_t n_first, int32_t* slots,
+                                  int32_t* cand, int32_t* cand_cnt, int64_t q) {
+  const float s4[4] = {s0, s1, s2, s3};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (s4[e] >= thr) {
+      int n = slots[kPend * kEpiThreads];
+      slots[n * kEpiThreads] = n_first + e;
+      slots[kPend * kEpiThreads] = ++n;
+      if (n == kPend) flush_pending(slots, cand, cand_cnt, q);
+    }
+  }
+}
+
+// One 128x64 half of an accumulator tile held by a thread as 64 registers.
+template <int PASS, bool PARTIAL>
+__device__ __forceinline__ void consume_tile(const float* v, float* cmax, float thr, int32_t n_first, int valid,
+                                             int32_t* slots, const PassParams& p, int64_t q) {
+  // valid: number of in-range columns among this thread's 64 (only read when PARTIAL)
+  if constexpr (PASS == 1) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+      const float s = (PARTIAL && j >= valid) ? kEmptyNh : v[j];
+      cmax[j] = fmaxf(cmax[j], s);
+    }
+  } else {
+#pragma unroll
+    for (int j4 = 0; j4 < 16; ++j4) {
+      float s4[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s4[e] = (PARTIAL && j4 * 4 + e >= valid) ? kEmptyNh : v[j4 * 4 + e];
+      const float m4 = fmaxf(fmaxf(s4[0], s4[1]), fmaxf(s4[2], s4[3]));
+      if (m4 >= thr) hit4(s4[0], s4[1], s4[2], s4[3], thr, n_first + j4 * 4, slots, p.cand, p.cand_cnt, q);
+    }
+  }
+}
+
 template <int PASS>
 __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -127,17 +186,16 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw);
   const uint32_t q_smem = base;
-  const uint32_t stage0 = base + kTileSmemStride;
-  const uint32_t bars = base + kTileSmemStride * (1 + kStages);
-  // barrier slots (8 B each)
-  const uint32_t bar_full = bars;                               // [kStages]
-  const uint32_t bar_empty = bars + 8 * kStages;                // [kStages]
-  const uint32_t bar_acc_full = bars + 16 * kStages;            // [kAccStages]
-  const uint32_t bar_acc_empty = bar_acc_full + 8 * kAccStages; // [kAccStages]
-  const uint32_t bar_q = bar_acc_empty + 8 * kAccStages;
-  const uint32_t tmem_slot = bar_q + 8;
+  const uint32_t stage0 = base + kTileBytes;
+  const uint32_t bars = base + kTileBytes * (1 + kStages);
+  const uint32_t bar_full = bars;                                // [kStages]
+  const uint32_t bar_empty = bars + 8 * kStages;                 // [kStages]
+  const uint32_t bar_acc_full = bars + 16 * kStages;             // [kAccStages]
+  const uint32_t bar_acc_empty = bar_acc_full + 8 * kAccStages;  // [kAccStages]
+  const uint32_t tmem_slot = bar_acc_empty + 8 * kAccStages;
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + kTileSmemStride * (1 + kStages) + 16 * kStages + 16 * kAccStages + 8);
+      reinterpret_cast<volatile uint32_t*>(base_ptr + kTileBytes * (1 + kStages) + 16 * kStages + 16 * kAccStages);
+  int32_t* pend_smem = reinterpret_cast<int32_t*>(base_ptr + kTileBytes * (1 + kStages) + kBarBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x % p.n_mtiles;
@@ -149,19 +207,43 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 8);
+      mbar_init(bar_empty + 8 * s, 1);
     }
     for (int a = 0; a < kAccStages; ++a) {
       mbar_init(bar_acc_full + 8 * a, 1);
       mbar_init(bar_acc_empty + 8 * a, 8);
     }
-    mbar_init(bar_q, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // Query tile: 128 rows x 64 channels fp32 -> bf16, 128B-swizzled K-major, + the (1,1,1,0..) slice.
+  {
+    uint8_t* qt = base_ptr;
+    const int64_t q0 = (int64_t)m_tile * 128;
+    for (int e = threadIdx.x; e < 128 * 32; e += kThreads) {
+      const int r = e & 127, cp = e >> 7;  // channel pair cp: channels 2cp, 2cp+1
+      float a = 0.f, b = 0.f;
+      if (q0 + r < p.n_query) {
+        a = __ldg(p.query + (int64_t)(2 * cp) * p.query_ch_stride + q0 + r);
+        b = __ldg(p.query + (int64_t)(2 * cp + 1) * p.query_ch_stride + q0 + r);
+      }
+      const __nv_bfloat162 v2 = __floats2bfloat162_rn(a, b);
+      *reinterpret_cast<__nv_bfloat162*>(qt + swizzle128_offset(r, cp >> 2) + (cp & 3) * 4) = v2;
+    }
+    for (int e = threadIdx.x; e < 128 * 2; e += kThreads) {
+      const int r = e >> 1, h = e & 1;
+      uint4 w = make_uint4(0, 0, 0, 0);
+      if (h == 0 && q0 + r < p.n_query) {
+        w.x = 0x3f803f80u;  // bf16 (1, 1)
+        w.y = 0x00003f80u;  // bf16 (1, 0)
+      }
+      *reinterpret_cast<uint4*>(qt + kTileKeyBytes + swizzle32_offset(r, h)) = w;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tcgen05 (async proxy)
   }
   tc_fence_before();
   __syncthreads();
@@ -171,46 +253,50 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar_q, kTileBytes);
-      bulk_g2s(q_smem, p.q_tiles + (int64_t)m_tile * kTileBytes, kTileBytes, bar_q);
       for (int i = 0; i < n_tiles; ++i) {
         const int s = i % kStages;
         const uint32_t ph = (uint32_t)((i / kStages) & 1);
         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
         mbar_arrive_expect_tx(bar_full + 8 * s, kTileBytes);
-        bulk_g2s(stage0 + s * kTileSmemStride, p.key_tiles + (int64_t)(t0 + i) * kTileBytes, kTileBytes,
-                 bar_full + 8 * s);
+        bulk_g2s(stage0 + s * kTileBytes, p.key_tiles + (int64_t)(t0 + i) * kTileBytes, kTileBytes, bar_full + 8 * s);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    mbar_wait(bar_q, 0);
-    const uint64_t adesc0 = make_sw128_desc(q_smem);
+    const uint64_t adesc0 = make_desc(q_smem, 1024, kLayoutSw128);
+    const uint64_t adesc_aug = make_desc(q_smem + kTileKeyBytes, 256, kLayoutSw32);
     for (int i = 0; i < n_tiles; ++i) {
       const int s = i % kStages, a = i % kAccStages;
       mbar_wait(bar_full + 8 * s, (uint32_t)((i / kStages) & 1));
       mbar_wait(bar_acc_empty + 8 * a, (uint32_t)(((i / kAccStages) & 1) ^ 1));
       tc_fence_after();
       if (lane == 0) {
-        const uint64_t bdesc0 = make_sw128_desc(stage0 + s * kTileSmemStride);
+        const uint32_t st = stage0 + s * kTileBytes;
+        const uint64_t bdesc0 = make_desc(st, 1024, kLayoutSw128);
+        const uint64_t bdesc_aug = make_desc(st + kTileKeyBytes, 256, kLayoutSw32);
+        const uint32_t d = tmem_base + a * 128;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 B): advance 2 x 16-byte units inside the swizzle atom
-          umma_bf16(tmem_base + a * 128, adesc0 + 2 * k, bdesc0 + 2 * k, kInstrDesc, k > 0 ? 1u : 0u);
-        umma_commit(bar_acc_full + 8 * a);
+        for (int k = 0; k < 4; ++k)  // K = 16 bf16 = 32 B per MMA: advance 2 x 16-byte units inside the swizzle atom
+          umma_bf16(d, adesc0 + 2 * k, bdesc0 + 2 * k, kInstrDesc, k > 0 ? 1u : 0u);
+        umma_bf16(d, adesc_aug, bdesc_aug, kInstrDesc, 1u);  // += -|k|^2/2
+        umma_commit(bar_empty + 8 * s);      // smem stage free once these MMAs have read it
+        umma_commit(bar_acc_full + 8 * a);   // accumulator tile complete
       }
       __syncwarp();
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> running class max / candidate append =====
     const int ew = warp - 4;
-    const int quarter = ew & 3;              // TMEM lane quarter this warp may access
-    const int col0 = (ew >> 2) * 64;         // accumulator columns of this warpgroup
+    const int quarter = ew & 3;       // TMEM lane quarter this warp may access
+    const int col0 = (ew >> 2) * 64;  // accumulator columns of this warpgroup
     const int row = quarter * 32 + lane;
     const int64_t q = (int64_t)m_tile * 128 + row;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
 
     float cmax[PASS == 1 ? 64 : 1];
     float thr = INFINITY;
+    int32_t* slots = pend_smem + (threadIdx.x - 128);
+    slots[kPend * kEpiThreads] = 0;
     if constexpr (PASS == 1) {
 #pragma unroll
       for (int j = 0; j < 64; ++j) cmax[j] = kEmptyNh;
@@ -219,50 +305,22 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
     }
 
     for (int i = 0; i < n_tiles; ++i) {
-      const int s = i % kStages, a = i % kAccStages;
+      const int a = i % kAccStages;
       mbar_wait(bar_acc_full + 8 * a, (uint32_t)((i / kAccStages) & 1));
-      mbar_wait(bar_full + 8 * s, (uint32_t)((i / kStages) & 1));  // makes the TMA-written -|k|^2/2 visible
       tc_fence_after();
-      const int64_t n0 = (int64_t)(t0 + i) * kTilePos;
-      const bool partial = n0 + kTilePos > p.n_pos;
-      const float* nh_s =
-          reinterpret_cast<const float*>(base_ptr + kTileSmemStride * (1 + s) + kTileKeyBytes) + col0;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float v[32];
-        tmem_ld32(lane_addr + (uint32_t)(a * 128 + col0 + h * 32), v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 nh = *reinterpret_cast<const float4*>(nh_s + h * 32 + j4 * 4);
-          float s4[4] = {v[j4 * 4 + 0] + nh.x, v[j4 * 4 + 1] + nh.y, v[j4 * 4 + 2] + nh.z, v[j4 * 4 + 3] + nh.w};
-          if (partial) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (n0 + col0 + h * 32 + j4 * 4 + e >= p.n_pos) s4[e] = kEmptyNh;
-          }
-          if constexpr (PASS == 1) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) cmax[h * 32 + j4 * 4 + e] = fmaxf(cmax[h * 32 + j4 * 4 + e], s4[e]);
-          } else {
-            const float m4 = fmaxf(fmaxf(s4[0], s4[1]), fmaxf(s4[2], s4[3]));
-            if (m4 >= thr) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (s4[e] >= thr) {
-                  const int pos = atomicAdd(p.cand_cnt + q, 1);
-                  if (pos < kCandCap) p.cand[q * kCandCap + pos] = (int32_t)(n0 + col0 + h * 32 + j4 * 4 + e);
-                }
-              }
-            }
-          }
-        }
-      }
+      float v[64];
+      tmem_ld32(lane_addr + (uint32_t)(a * 128 + col0), v);
+      tmem_ld32(lane_addr + (uint32_t)(a * 128 + col0 + 32), v + 32);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar_acc_empty + 8 * a);
-        mbar_arrive(bar_empty + 8 * s);
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * a);  // registers hold the tile: release the TMEM stage
+      const int64_t n0 = (int64_t)(t0 + i) * kTilePos + col0;
+      if (n0 + 64 > p.n_pos) {
+        const int valid = (int)max((int64_t)0, p.n_pos - n0);
+        consume_tile<PASS, true>(v, cmax, thr, (int32_t)n0, valid, slots, p, q);
+      } else {
+        consume_tile<PASS, false>(v, cmax, thr, (int32_t)n0, 64, slots, p, q);
       }
     }
 
@@ -271,6 +329,8 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
 #pragma unroll
       for (int j4 = 0; j4 < 16; ++j4)
         dst[j4] = make_float4(cmax[j4 * 4], cmax[j4 * 4 + 1], cmax[j4 * 4 + 2], cmax[j4 * 4 + 3]);
+    } else {
+      flush_pending(slots, p.cand, p.cand_cnt, q);
     }
   }
 
@@ -284,32 +344,21 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
 
 }  // namespace
 
-// Number of memory-axis chunks: CTAs = m_tiles * chunks should fill whole waves of n_sm.
+// Memory-axis chunks per query tile: one wave of CTAs (m_tiles * chunks <= n_sm) whenever possible.
 int score_pass_chunks(int64_t n_pos, int64_t n_query, int n_sm) {
   const int64_t mt = ceil_div(n_query, 128), nt = ceil_div(n_pos, kTilePos);
-  int64_t g_max = (4 * (int64_t)n_sm) / mt;
-  if (g_max < 1) g_max = 1;
-  if (g_max > nt) g_max = nt;
-  int best = 1;
-  double best_eff = -1.0;
-  for (int64_t g = 1; g <= g_max; ++g) {
-    const int64_t ctas = mt * g;
-    const int64_t waves = ceil_div(ctas, n_sm);
-    double eff = (double)ctas / (double)(waves * n_sm);
-    if (nt / g < 2) eff -= 0.25;  // keep at least two tiles per CTA to amortise the prologue
-    if (eff > best_eff + 1e-9) {
-      best_eff = eff;
-      best = (int)g;
-    }
-  }
-  return best;
+  int64_t g = n_sm / mt;
+  if (g < 1) g = 1;
+  if (g > nt) g = nt;
+  return (int)g;
 }
 
-int launch_score_pass(int pass, const void* q_tiles, const void* key_tiles, int64_t n_pos, int64_t n_query,
-                      int n_chunks, float* class_max, const float* tau, int32_t* cand, int32_t* cand_cnt,
-                      cudaStream_t st) {
+int launch_score_pass(int pass, const float* query, int64_t query_ch_stride, const void* key_tiles, int64_t n_pos,
+                      int64_t n_query, int n_chunks, float* class_max, const float* tau, int32_t* cand,
+                      int32_t* cand_cnt, cudaStream_t st) {
   PassParams p;
-  p.q_tiles = reinterpret_cast<const uint8_t*>(q_tiles);
+  p.query = query;
+  p.query_ch_stride = query_ch_stride;
   p.key_tiles = reinterpret_cast<const uint8_t*>(key_tiles);
   p.n_pos = n_pos;
   p.n_query = n_query;

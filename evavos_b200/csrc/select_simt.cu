@@ -70,9 +70,9 @@ __device__ __forceinline__ void score_group(const float* __restrict__ key_pm, in
 }
 
 __global__ void __launch_bounds__(256) brute_select_kernel(
-    const float* __restrict__ key_pm, const float* __restrict__ q_pm, int CK, int64_t n_pos, int64_t n_query,
-    int top_k, const int32_t* __restrict__ work_list, const int32_t* __restrict__ work_cnt,
-    int32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt) {
+    const float* __restrict__ key_pm, const float* __restrict__ query, int64_t query_ch_stride, int CK,
+    int64_t n_pos, int64_t n_query, int top_k, int only_overflow, int32_t* __restrict__ cand,
+    int32_t* __restrict__ cand_cnt) {
   __shared__ __align__(16) float qs[kBruteQ][64];
   __shared__ float qq[kBruteQ];
   __shared__ int qid[kBruteQ];
@@ -84,8 +84,7 @@ __global__ void __launch_bounds__(256) brute_select_kernel(
   __shared__ int warp_eq[8][kBruteQ];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t n_work = work_cnt ? (int64_t)*work_cnt : n_query;
-  const int64_t groups = (n_work + kBruteQ - 1) / kBruteQ;
+  const int64_t groups = (n_query + kBruteQ - 1) / kBruteQ;
   const float inv_sqrt_ck = 1.0f / sqrtf((float)CK);
 
   for (int64_t grp = blockIdx.x; grp < groups; grp += gridDim.x) {
@@ -93,7 +92,7 @@ __global__ void __launch_bounds__(256) brute_select_kernel(
     if (tid < kBruteQ) {
       const int64_t w = grp * kBruteQ + tid;
       int q = -1;
-      if (w < n_work) q = work_list ? work_list[w] : (int)w;
+      if (w < n_query && (!only_overflow || cand_cnt[w] > kCandCap)) q = (int)w;
       qid[tid] = q;
       remaining[tid] = top_k;
       prefix[tid] = 0;
@@ -101,10 +100,16 @@ __global__ void __launch_bounds__(256) brute_select_kernel(
       eq_base[tid] = 0;
     }
     __syncthreads();
+    {
+      bool any = false;
+#pragma unroll
+      for (int j = 0; j < kBruteQ; ++j) any |= qid[j] >= 0;
+      if (!any) continue;  // uniform: nothing overflowed in this group
+    }
     for (int e = tid; e < kBruteQ * 64; e += 256) {
       const int j = e >> 6, c = e & 63;
       const int q = qid[j];
-      qs[j][c] = (q >= 0 && c < CK) ? q_pm[(int64_t)q * CK + c] : 0.f;
+      qs[j][c] = (q >= 0 && c < CK) ? query[(int64_t)c * query_ch_stride + q] : 0.f;
     }
     __syncthreads();
     if (tid < kBruteQ) qq[tid] = sumsq(qs[tid], CK);
@@ -193,28 +198,29 @@ __global__ void __launch_bounds__(256) brute_select_kernel(
   }
 }
 
-__global__ void overflow_list_kernel(const int32_t* __restrict__ cand_cnt, int64_t n_query,
-                                     int32_t* __restrict__ work_list, int32_t* __restrict__ work_cnt) {
-  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q < n_query && cand_cnt[q] > kCandCap) {
-    const int pos = atomicAdd(work_cnt, 1);
-    work_list[pos] = (int32_t)q;
-  }
-}
-
 // One warp per query: k-th largest of 128 class maxima by bitwise radix descent.
 __global__ void __launch_bounds__(128) threshold_kernel(
     const float* __restrict__ class_max, int n_chunks, int64_t n_query, int64_t nq_pad, int top_k,
-    const uint8_t* __restrict__ q_tiles, const float* __restrict__ key_maxnorm, float* __restrict__ tau,
-    int32_t* __restrict__ cand_cnt) {
+    const float* __restrict__ query, int64_t query_ch_stride, const float* __restrict__ key_maxnorm,
+    float* __restrict__ tau, int32_t* __restrict__ cand_cnt) {
   const int lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (q >= n_query) return;
   float v[4] = {kEmptyNh, kEmptyNh, kEmptyNh, kEmptyNh};
+#pragma unroll 4
   for (int g = 0; g < n_chunks; ++g) {
     const float* row = class_max + ((int64_t)g * nq_pad + q) * 128;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) v[t] = fmaxf(v[t], row[lane + 32 * t]);
+    for (int t = 0; t < 4; ++t) v[t] = fmaxf(v[t], __ldg(row + lane + 32 * t));
+  }
+  // |q|^2 over the 64 key channels (two per lane)
+  float qsq = 0.f;
+  {
+    const float a = __ldg(query + (int64_t)lane * query_ch_stride + q);
+    const float b = __ldg(query + (int64_t)(lane + 32) * query_ch_stride + q);
+    qsq = fmaf(a, a, b * b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qsq += __shfl_xor_sync(0xffffffffu, qsq, o);
   }
   uint32_t key[4];
 #pragma unroll
@@ -229,9 +235,7 @@ __global__ void __launch_bounds__(128) threshold_kernel(
   }
   if (lane == 0) {
     const float kth = ordered_to_float(pfx);
-    const float nhq = *reinterpret_cast<const float*>(q_tiles + (q / kTilePos) * (int64_t)kTileBytes +
-                                                      kTileKeyBytes + (q % kTilePos) * 4);
-    const float qn = sqrtf(fmaxf(-2.0f * nhq, 0.f));
+    const float qn = sqrtf(qsq) * 1.0001f;
     const float kn = *key_maxnorm;
     // |q^.k^ - q.k| <= 2^-8 (1 + 2^-10) |q||k| for bf16 round-to-nearest operands, plus slack for the
     // tensor-core fp32 accumulation and the rounding of -|k|^2/2.
@@ -241,55 +245,52 @@ __global__ void __launch_bounds__(128) threshold_kernel(
   }
 }
 
-// One warp per query, 4 warps per CTA.
+// One warp per query, 4 warps per CTA.  Candidates are rescored exactly, ranked all-pairs
+// (rank = number of candidates with a larger (score, -position) key), and the first top_k ranks
+// are written best-first with their softmax weights.
 __global__ void __launch_bounds__(128) finalize_kernel(
-    const float* __restrict__ key_pm, const float* __restrict__ q_pm, int CK, int64_t n_query, int top_k,
-    const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt, int32_t* __restrict__ out_idx,
-    float* __restrict__ out_weight, float* __restrict__ out_score) {
+    const float* __restrict__ key_pm, const float* __restrict__ query, int64_t query_ch_stride, int CK,
+    int64_t n_query, int top_k, const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
+    int32_t* __restrict__ out_idx, float* __restrict__ out_weight, float* __restrict__ out_score) {
   __shared__ __align__(16) float qs_all[4][64];
+  __shared__ unsigned long long keys_all[4][kCandCap];
   __shared__ unsigned long long sel_all[4][EVAVOS_MAX_TOPK];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t q = (int64_t)blockIdx.x * 4 + warp;
   if (q >= n_query) return;
   float* qs = qs_all[warp];
+  unsigned long long* keys = keys_all[warp];
   unsigned long long* sel = sel_all[warp];
-  for (int c = lane; c < 64; c += 32) qs[c] = (c < CK) ? q_pm[q * CK + c] : 0.f;
+  for (int c = lane; c < 64; c += 32) qs[c] = (c < CK) ? __ldg(query + (int64_t)c * query_ch_stride + q) : 0.f;
   __syncwarp();
   const float qq = sumsq(qs, CK);
   const float inv_sqrt_ck = 1.0f / sqrtf((float)CK);
   const int cnt = min(cand_cnt[q], kCandCap);
+  const int slots = (cnt + 31) >> 5;  // warp-uniform
 
-  constexpr int kPerLane = kCandCap / 32;
-  unsigned long long key[kPerLane];
-#pragma unroll
-  for (int t = 0; t < kPerLane; ++t) {
+  for (int t = 0; t < slots; ++t) {
     const int ci = lane + 32 * t;
-    key[t] = 0ull;
+    unsigned long long key = 0ull;
     if (ci < cnt) {
       const int32_t n = cand[q * kCandCap + ci];
       float kk, kq;
       dot_row(reinterpret_cast<const float4*>(key_pm + (int64_t)n * CK), qs, CK, kk, kq);
       const float s = affinity_from_parts(kk, kq, qq, inv_sqrt_ck);
-      key[t] = ((unsigned long long)float_to_ordered(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
+      key = ((unsigned long long)float_to_ordered(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
     }
-  }
-  const int take = min(top_k, cnt);
-  for (int j = 0; j < take; ++j) {
-    unsigned long long best = key[0];
-#pragma unroll
-    for (int t = 1; t < kPerLane; ++t) best = key[t] > best ? key[t] : best;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-      best = other > best ? other : best;
-    }
-#pragma unroll
-    for (int t = 0; t < kPerLane; ++t)
-      if (key[t] == best) key[t] = 0ull;
-    if (lane == 0) sel[j] = best;
+    keys[ci] = key;
   }
   __syncwarp();
-  const float s0 = ordered_to_float((uint32_t)(sel[0] >> 32));
+  const int take = min(top_k, cnt);
+  for (int t = 0; t < slots; ++t) {
+    const int ci = lane + 32 * t;
+    const unsigned long long mine = keys[ci];
+    int rank = 0;
+    for (int j = 0; j < cnt; ++j) rank += keys[j] > mine ? 1 : 0;  // broadcast reads; keys are unique
+    if (ci < cnt && rank < take) sel[rank] = mine;
+  }
+  __syncwarp();
+  const float s0 = take > 0 ? ordered_to_float((uint32_t)(sel[0] >> 32)) : 0.f;
   float e[EVAVOS_MAX_TOPK / 32];
   float part = 0.f;
 #pragma unroll
@@ -318,42 +319,33 @@ __global__ void __launch_bounds__(128) finalize_kernel(
 
 }  // namespace
 
-int launch_brute_select(const float* key_pm, const float* q_pm, int CK, int64_t n_pos, int64_t n_query,
-                        int top_k, const int32_t* work_list, const int32_t* work_cnt, int32_t* cand,
-                        int32_t* cand_cnt, int n_sm, cudaStream_t st) {
+int launch_brute_select(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_pos,
+                        int64_t n_query, int top_k, int only_overflow, int32_t* cand, int32_t* cand_cnt, int n_sm,
+                        cudaStream_t st) {
   int64_t grid = ceil_div(n_query, kBruteQ);
   const int64_t cap = (int64_t)n_sm * 8;  // 8 resident 256-thread CTAs per SM
-  if (work_list != nullptr && grid > cap) grid = cap;
+  if (only_overflow && grid > cap) grid = cap;
   if (grid > 0x7fffffff) grid = 0x7fffffff;
-  brute_select_kernel<<<(unsigned)grid, 256, 0, st>>>(key_pm, q_pm, CK, n_pos, n_query, top_k, work_list,
-                                                      work_cnt, cand, cand_cnt);
-  EVAVOS_CUDA_OK(cudaGetLastError());
-  return EVAVOS_OK;
-}
-
-int launch_overflow_list(const int32_t* cand_cnt, int64_t n_query, int32_t* work_list, int32_t* work_cnt,
-                         cudaStream_t st) {
-  EVAVOS_CUDA_OK(cudaMemsetAsync(work_cnt, 0, sizeof(int32_t), st));
-  overflow_list_kernel<<<(unsigned)ceil_div(n_query, 256), 256, 0, st>>>(cand_cnt, n_query, work_list, work_cnt);
+  brute_select_kernel<<<(unsigned)grid, 256, 0, st>>>(key_pm, query, query_ch_stride, CK, n_pos, n_query, top_k,
+                                                      only_overflow, cand, cand_cnt);
   EVAVOS_CUDA_OK(cudaGetLastError());
   return EVAVOS_OK;
 }
 
 int launch_threshold(const float* class_max, int n_chunks, int64_t n_query, int64_t nq_pad, int top_k,
-                     const void* q_tiles, const float* key_maxnorm, float* tau, int32_t* cand_cnt,
-                     cudaStream_t st) {
-  threshold_kernel<<<(unsigned)ceil_div(n_query, 4), 128, 0, st>>>(
-      class_max, n_chunks, n_query, nq_pad, top_k, reinterpret_cast<const uint8_t*>(q_tiles), key_maxnorm, tau,
-      cand_cnt);
+                     const float* query, int64_t query_ch_stride, const float* key_maxnorm, float* tau,
+                     int32_t* cand_cnt, cudaStream_t st) {
+  threshold_kernel<<<(unsigned)ceil_div(n_query, 4), 128, 0, st>>>(class_max, n_chunks, n_query, nq_pad, top_k, query,
+                                                                  query_ch_stride, key_maxnorm, tau, cand_cnt);
   EVAVOS_CUDA_OK(cudaGetLastError());
   return EVAVOS_OK;
 }
 
-int launch_finalize(const float* key_pm, const float* q_pm, int CK, int64_t n_query, int top_k,
-                    const int32_t* cand, const int32_t* cand_cnt, int32_t* out_idx, float* out_weight,
+int launch_finalize(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_query,
+                    int top_k, const int32_t* cand, const int32_t* cand_cnt, int32_t* out_idx, float* out_weight,
                     float* out_score, cudaStream_t st) {
-  finalize_kernel<<<(unsigned)ceil_div(n_query, 4), 128, 0, st>>>(key_pm, q_pm, CK, n_query, top_k, cand,
-                                                                  cand_cnt, out_idx, out_weight, out_score);
+  finalize_kernel<<<(unsigned)ceil_div(n_query, 4), 128, 0, st>>>(key_pm, query, query_ch_stride, CK, n_query, top_k,
+                                                                  cand, cand_cnt, out_idx, out_weight, out_score);
   EVAVOS_CUDA_OK(cudaGetLastError());
   return EVAVOS_OK;
 }

@@ -43,7 +43,9 @@
  *   key_pm     [n_pos][CK] fp32            exact keys, one 4*CK-byte row per position
  *   key_tiles  ceil(n_pos/128) tile images of EVAVOS_TILE_BYTES each: 128 bf16 key rows
  *              in the 128B-swizzled K-major shared-memory layout tcgen05.mma consumes,
- *              followed by 128 fp32 values -|k|^2/2 (loaded verbatim by one bulk TMA copy)
+ *              followed by a 16-wide extra K slice per row (bf16 hi/mid/lo split of -|k|^2/2,
+ *              32B-swizzled) so the norm term is part of the contraction; one tile image is
+ *              loaded verbatim by one bulk TMA copy
  *   key_maxnorm  1 fp32: max |k| over the bank (rigorous bf16 error bound for the filter)
  *   val_pm     [K][n_pos][CV] fp32 or bf16 value rows
  */
@@ -74,7 +76,7 @@ extern "C" {
 #define EVAVOS_PATH_SIMT 2   /* exact fp32 CUDA-core radix select (also the overflow path)    */
 
 #define EVAVOS_TILE_POS 128      /* memory positions per key tile image  */
-#define EVAVOS_TILE_BYTES 16896  /* 128 rows x 128 B (bf16, CK=64) + 128 x 4 B               */
+#define EVAVOS_TILE_BYTES 20480  /* 128 rows x 128 B (bf16 keys, CK=64) + 128 rows x 32 B (-|k|^2/2) */
 #define EVAVOS_MAX_TOPK 128
 
 typedef void* evavos_stream_t; /* cudaStream_t */
@@ -82,7 +84,7 @@ typedef void* evavos_stream_t; /* cudaStream_t */
 /* Engine-private shadow of a memory bank (all device pointers). */
 typedef struct EvavosBankShadow {
   float* key_pm;       /* [capacity_pos][CK] fp32                                   */
-  void* key_tiles;     /* ceil(capacity_pos/128) * EVAVOS_TILE_BYTES, 1024B aligned; NULL when CK != 64 */
+  void* key_tiles;     /* ceil(capacity_pos/128) * EVAVOS_TILE_BYTES, 16B aligned; NULL when CK != 64 */
   float* key_maxnorm;  /* 1 fp32, must be zero-initialised by the caller             */
   void* val_pm;        /* [K][capacity_pos][CV] of val_dtype                         */
   int64_t capacity_pos; /* positions the buffers were sized for                      */
