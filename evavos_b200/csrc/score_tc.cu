@@ -33,7 +33,7 @@ constexpr int kThreads = 384;
 constexpr int kEpiThreads = 256;
 constexpr int kPend = 8;  // private candidate slots per epilogue thread before a flush
 constexpr int kBarBytes = 256;
-constexpr int kSmemBytes = kTileBytes * (1 + kStages) + kBarBytes + (kPend + 1) * kEpiThreads * 4 + 1024;
+constexpr int kSmemBytes = kTileBytes * (1 + kStages) + kBarBytes + kPend * kEpiThreads * 4 + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -131,35 +131,19 @@ struct PassParams {
   int32_t* cand_cnt;
 };
 
-// Candidate append of pass 2: private shared-memory slots (slot e of a thread at slots[e * kEpiThreads],
-// its fill count at slots[kPend * kEpiThreads]), one global atomic per kPend hits.  Kept out of line:
-// hits are rare (about top_k + margin per query over the whole bank) and the hot loop stays small.
-__device__ __noinline__ void flush_pending(int32_t* slots, int32_t* cand, int32_t* cand_cnt, int64_t q) {
-  const int n = slots[kPend * kEpiThreads];
-  if (n == 0) return;
+// Candidate append of pass 2: private shared-memory slots (slot e of a thread at slots[e * kEpiThreads]),
+// flushed to the query's global list with one atomic.  Hits are rare (about top_k + margin per query
+// over the whole bank), so the flush stays out of line and the hot loop small.
+__device__ __noinline__ void flush_pending(const int32_t* slots, int n, int32_t* cand, int32_t* cand_cnt, int64_t q) {
   const int base = atomicAdd(cand_cnt + q, n);
   for (int e = 0; e < n; ++e)
     if (base + e < kCandCap) cand[q * kCandCap + base + e] = slots[e * kEpiThreads];
-  slots[kPend * kEpiThreads] = 0;
-}
-__device__ __noinline__ void hit4(float s0, float s1, float s2, float s3, float thr, int32_t n_first, int32_t* slots,
-                                  int32_t* cand, int32_t* cand_cnt, int64_t q) {
-  const float s4[4] = {s0, s1, s2, s3};
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    if (s4[e] >= thr) {
-      int n = slots[kPend * kEpiThreads];
-      slots[n * kEpiThreads] = n_first + e;
-      slots[kPend * kEpiThreads] = ++n;
-      if (n == kPend) flush_pending(slots, cand, cand_cnt, q);
-    }
-  }
 }
 
 // One 128x64 half of an accumulator tile held by a thread as 64 registers.
 template <int PASS, bool PARTIAL>
 __device__ __forceinline__ void consume_tile(const float* v, float* cmax, float thr, int32_t n_first, int valid,
-                                             int32_t* slots, const PassParams& p, int64_t q) {
+                                             int32_t* slots, int& pending, const PassParams& p, int64_t q) {
   // valid: number of in-range columns among this thread's 64 (only read when PARTIAL)
   if constexpr (PASS == 1) {
 #pragma unroll
@@ -174,7 +158,19 @@ __device__ __forceinline__ void consume_tile(const float* v, float* cmax, float 
 #pragma unroll
       for (int e = 0; e < 4; ++e) s4[e] = (PARTIAL && j4 * 4 + e >= valid) ? kEmptyNh : v[j4 * 4 + e];
       const float m4 = fmaxf(fmaxf(s4[0], s4[1]), fmaxf(s4[2], s4[3]));
-      if (m4 >= thr) hit4(s4[0], s4[1], s4[2], s4[3], thr, n_first + j4 * 4, slots, p.cand, p.cand_cnt, q);
+      if (m4 >= thr) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (s4[e] >= thr) {
+            slots[pending * kEpiThreads] = n_first + j4 * 4 + e;
+            ++pending;
+          }
+        }
+        if (pending > kPend - 4) {  // the next group of 4 must always fit
+          flush_pending(slots, pending, p.cand, p.cand_cnt, q);
+          pending = 0;
+        }
+      }
     }
   }
 }
@@ -220,19 +216,38 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // The first ring of key tiles does not depend on anything below: get it in flight now.
+  if (threadIdx.x == 0) {
+    const int pre = n_tiles < kStages ? n_tiles : kStages;
+    for (int i = 0; i < pre; ++i) {
+      mbar_arrive_expect_tx(bar_full + 8 * i, kTileBytes);
+      bulk_g2s(stage0 + i * kTileBytes, p.key_tiles + (int64_t)(t0 + i) * kTileBytes, kTileBytes, bar_full + 8 * i);
+    }
+  }
   // Query tile: 128 rows x 64 channels fp32 -> bf16, 128B-swizzled K-major, + the (1,1,1,0..) slice.
   {
     uint8_t* qt = base_ptr;
     const int64_t q0 = (int64_t)m_tile * 128;
-    for (int e = threadIdx.x; e < 128 * 32; e += kThreads) {
+    constexpr int kPairs = 128 * 32, kIters = (kPairs + kThreads - 1) / kThreads;
+    float va[kIters], vb[kIters];
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {  // all loads first: one memory round trip for the whole tile
+      const int e = threadIdx.x + it * kThreads;
       const int r = e & 127, cp = e >> 7;  // channel pair cp: channels 2cp, 2cp+1
-      float a = 0.f, b = 0.f;
-      if (q0 + r < p.n_query) {
-        a = __ldg(p.query + (int64_t)(2 * cp) * p.query_ch_stride + q0 + r);
-        b = __ldg(p.query + (int64_t)(2 * cp + 1) * p.query_ch_stride + q0 + r);
+      va[it] = 0.f;
+      vb[it] = 0.f;
+      if (e < kPairs && q0 + r < p.n_query) {
+        va[it] = __ldg(p.query + (int64_t)(2 * cp) * p.query_ch_stride + q0 + r);
+        vb[it] = __ldg(p.query + (int64_t)(2 * cp + 1) * p.query_ch_stride + q0 + r);
       }
-      const __nv_bfloat162 v2 = __floats2bfloat162_rn(a, b);
-      *reinterpret_cast<__nv_bfloat162*>(qt + swizzle128_offset(r, cp >> 2) + (cp & 3) * 4) = v2;
+    }
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int e = threadIdx.x + it * kThreads;
+      const int r = e & 127, cp = e >> 7;
+      if (e < kPairs)
+        *reinterpret_cast<__nv_bfloat162*>(qt + swizzle128_offset(r, cp >> 2) + (cp & 3) * 4) =
+            __floats2bfloat162_rn(va[it], vb[it]);
     }
     for (int e = threadIdx.x; e < 128 * 2; e += kThreads) {
       const int r = e >> 1, h = e & 1;
@@ -253,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int i = 0; i < n_tiles; ++i) {
+      for (int i = kStages; i < n_tiles; ++i) {  // tiles [0, kStages) were issued in the prologue
         const int s = i % kStages;
         const uint32_t ph = (uint32_t)((i / kStages) & 1);
         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
@@ -296,7 +311,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
     float cmax[PASS == 1 ? 64 : 1];
     float thr = INFINITY;
     int32_t* slots = pend_smem + (threadIdx.x - 128);
-    slots[kPend * kEpiThreads] = 0;
+    int pending = 0;
     if constexpr (PASS == 1) {
 #pragma unroll
       for (int j = 0; j < 64; ++j) cmax[j] = kEmptyNh;
@@ -318,9 +333,9 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
       const int64_t n0 = (int64_t)(t0 + i) * kTilePos + col0;
       if (n0 + 64 > p.n_pos) {
         const int valid = (int)max((int64_t)0, p.n_pos - n0);
-        consume_tile<PASS, true>(v, cmax, thr, (int32_t)n0, valid, slots, p, q);
+        consume_tile<PASS, true>(v, cmax, thr, (int32_t)n0, valid, slots, pending, p, q);
       } else {
-        consume_tile<PASS, false>(v, cmax, thr, (int32_t)n0, 64, slots, p, q);
+        consume_tile<PASS, false>(v, cmax, thr, (int32_t)n0, 64, slots, pending, p, q);
       }
     }
 
@@ -330,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
       for (int j4 = 0; j4 < 16; ++j4)
         dst[j4] = make_float4(cmax[j4 * 4], cmax[j4 * 4 + 1], cmax[j4 * 4 + 2], cmax[j4 * 4 + 3]);
     } else {
-      flush_pending(slots, p.cand, p.cand_cnt, q);
+      if (pending > 0) flush_pending(slots, pending, p.cand, p.cand_cnt, q);
     }
   }
 

@@ -24,6 +24,20 @@ __device__ __forceinline__ void dot_row(const float4* __restrict__ krow, const f
                                         float& kk, float& kq) {
   kk = 0.f;
   kq = 0.f;
+  if (CK == 64) {  // the network's key width: all 16 row loads in flight before the first FMA
+    float4 kv[16];
+#pragma unroll
+    for (int c4 = 0; c4 < 16; ++c4) kv[c4] = __ldg(krow + c4);
+#pragma unroll
+    for (int c4 = 0; c4 < 16; ++c4) {
+      const float4 qv = *reinterpret_cast<const float4*>(q + 4 * c4);
+      kk = fmaf(kv[c4].x, kv[c4].x, kk); kq = fmaf(kv[c4].x, qv.x, kq);
+      kk = fmaf(kv[c4].y, kv[c4].y, kk); kq = fmaf(kv[c4].y, qv.y, kq);
+      kk = fmaf(kv[c4].z, kv[c4].z, kk); kq = fmaf(kv[c4].z, qv.z, kq);
+      kk = fmaf(kv[c4].w, kv[c4].w, kk); kq = fmaf(kv[c4].w, qv.w, kq);
+    }
+    return;
+  }
   for (int c4 = 0; c4 < (CK >> 2); ++c4) {
     const float4 kv = __ldg(krow + c4);
     const float4 qv = *reinterpret_cast<const float4*>(q + 4 * c4);
