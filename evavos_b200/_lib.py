@@ -19,7 +19,7 @@ MAX_TOPK = 128
 ERR_TOPK_RANGE = -5
 
 LIB_NAME = "libevavos_sm100.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+LIB_PATH = os.environ.get("EVAVOS_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 _c_i32, _c_i64, _c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
 

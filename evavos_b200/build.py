@@ -33,19 +33,21 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+    """trace=True builds libevavos_sm100_trace.so with -DEVAVOS_TRACE (kernel timeline, debugging only)."""
+    out = OUT.replace(".so", "_trace.so") if trace else OUT
+    if not force and not trace and not is_stale():
         return OUT
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DEVAVOS_TRACE"] if trace else []) + \
+          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libevavos_sm100.so")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, trace="--trace" in sys.argv)
     print(path)

@@ -77,6 +77,7 @@ struct SelectBuffers {
   float* tau;         // [nq_pad]
   int32_t* cand_cnt;  // [nq_pad]
   int32_t* cand;      // [nq_pad][kCandCap]
+  void* pending;      // pass-2 staging strips (score_pass_pending_bytes)
 };
 
 // The query is always addressed in the caller's layout: element (c, q) at query[c * query_ch_stride + q].
@@ -92,7 +93,8 @@ int launch_threshold(const float* class_max, int n_chunks, int64_t n_query, int6
                      int32_t* cand_cnt, cudaStream_t st);
 int launch_score_pass(int pass, const float* query, int64_t query_ch_stride, const void* key_tiles, int64_t n_pos,
                       int64_t n_query, int n_chunks, float* class_max, const float* tau, int32_t* cand,
-                      int32_t* cand_cnt, cudaStream_t st);
+                      int32_t* cand_cnt, void* pending, cudaStream_t st);
+size_t score_pass_pending_bytes(int64_t n_query, int n_chunks);
 int score_pass_chunks(int64_t n_pos, int64_t n_query, int n_sm);
 
 int launch_readout(const EvavosBankShadow& b, const int32_t* idx, const float* weight, int64_t n_query,

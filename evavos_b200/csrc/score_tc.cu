@@ -15,25 +15,37 @@
 //           error margin) is appended to the query's candidate list, which therefore
 //           contains the exact fp32 top-k.  finalize_kernel's exact rescoring picks it.
 //
-// Roles per CTA (384 threads, 1 CTA/SM, one wave): warp 0 = TMA producer (cp.async.bulk of
-// pre-swizzled 20 KB key tile images), warp 1 = MMA issuer (one elected lane, 5 x tcgen05.mma
-// 128x128x16 per tile), warp 2 = TMEM allocator, warps 4-11 = epilogue (two warpgroups, each thread
-// owns one query row and 64 accumulator columns).  Rings: 6 shared-memory key stages, 4 TMEM
+// Roles per CTA (640 threads, 1 CTA/SM, one wave): warps 0 and 3 = TMA producers (cp.async.bulk of
+// pre-swizzled 20 KB key tile images; one issuing thread sustains only ~50 B/clk, two reach the L2
+// rate), warp 1 = MMA issuer (one elected lane, 5 x tcgen05.mma 128x128x16 per tile), warp 2 = TMEM
+// allocator, warps 4-19 = epilogue (four warpgroups, each thread owns one query row and 32
+// accumulator columns; branch-free inner loops).  Rings: 6 shared-memory key stages, 4 TMEM
 // accumulator stages (4 x 128 columns = all 512).  The query tile is converted to bf16 and
 // swizzled into shared memory by the CTA itself.
 #include "common.cuh"
 
 namespace evavos {
 
+#ifdef EVAVOS_TRACE
+// Timeline of CTA 0 (clock64): rows = producer issue, MMA waits done, MMA issued, epilogue acc_full seen,
+// epilogue TMEM load done, epilogue math done; columns = tile index (first 64 tiles).
+__device__ long long g_trace[6][64];
+#define EVAVOS_TR(row, i) do { if (blockIdx.x == 0 && (i) < 64) g_trace[row][i] = clock64(); } while (0)
+#else
+#define EVAVOS_TR(row, i) do { } while (0)
+#endif
+
 namespace {
 
-constexpr int kStages = 6;
-constexpr int kAccStages = 4;
-constexpr int kThreads = 384;
-constexpr int kEpiThreads = 256;
-constexpr int kPend = 8;  // private candidate slots per epilogue thread before a flush
+constexpr int kStages = 8;
+constexpr int kAccStages = 3;   // 3 x 128 accumulator columns; the query operand lives in columns [384, 424)
+constexpr int kQueryCol = 384;
+constexpr int kThreads = 640;
+constexpr int kEpiThreads = 512;
+constexpr int kCols = 32;       // accumulator columns per epilogue thread
+constexpr int kPend = 16;       // staged hit groups per epilogue thread (flushed when more than half full)
 constexpr int kBarBytes = 256;
-constexpr int kSmemBytes = kTileBytes * (1 + kStages) + kBarBytes + kPend * kEpiThreads * 4 + 1024;
+constexpr int kSmemBytes = kTileBytes * kStages + kBarBytes + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -79,6 +91,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// Same with A taken from TMEM (128 lanes x 8 columns of packed bf16 pairs per K = 16 step).
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -129,47 +156,58 @@ struct PassParams {
   const float* tau;
   int32_t* cand;
   int32_t* cand_cnt;
+  float4* pend_score;   // [grid][kPend][kEpiThreads] scores of staged hit groups (pass 2)
+  int32_t* pend_pos;    // [grid][kPend][kEpiThreads] first position of each staged group
 };
 
-// Candidate append of pass 2: private shared-memory slots (slot e of a thread at slots[e * kEpiThreads]),
-// flushed to the query's global list with one atomic.  Hits are rare (about top_k + margin per query
-// over the whole bank), so the flush stays out of line and the hot loop small.
-__device__ __noinline__ void flush_pending(const int32_t* slots, int n, int32_t* cand, int32_t* cand_cnt, int64_t q) {
-  const int base = atomicAdd(cand_cnt + q, n);
-  for (int e = 0; e < n; ++e)
-    if (base + e < kCandCap) cand[q * kCandCap + base + e] = slots[e * kEpiThreads];
+// Pass 2 stages every group of 4 adjacent scores whose maximum reaches the threshold (scores + first
+// position, two predicated stores, no branch) in a private strip of the workspace; the strip is resolved
+// into the query's candidate list out of line.  Hits are rare: about top_k + margin per query over the
+// whole bank.
+__device__ __noinline__ void flush_pending(const float4* ps, const int32_t* pp, int n, float thr, int32_t* cand,
+                                           int32_t* cand_cnt, int64_t q) {
+  int hits = 0;
+  for (int e = 0; e < n; ++e) {
+    const float4 s = ps[e * kEpiThreads];
+    hits += (s.x >= thr) + (s.y >= thr) + (s.z >= thr) + (s.w >= thr);
+  }
+  int at = atomicAdd(cand_cnt + q, hits);
+  for (int e = 0; e < n; ++e) {
+    const float4 s = ps[e * kEpiThreads];
+    const int32_t n0 = pp[e * kEpiThreads];
+    const float v[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (v[k] >= thr) {
+        if (at < kCandCap) cand[q * kCandCap + at] = n0 + k;
+        ++at;
+      }
+    }
+  }
 }
 
-// One 128x64 half of an accumulator tile held by a thread as 64 registers.
+// 32 accumulator columns of one query row, held as registers.
 template <int PASS, bool PARTIAL>
 __device__ __forceinline__ void consume_tile(const float* v, float* cmax, float thr, int32_t n_first, int valid,
-                                             int32_t* slots, int& pending, const PassParams& p, int64_t q) {
-  // valid: number of in-range columns among this thread's 64 (only read when PARTIAL)
+                                             float4* ps, int32_t* pp, int& pending) {
+  // valid: number of in-range columns among this thread's kCols (only read when PARTIAL)
   if constexpr (PASS == 1) {
 #pragma unroll
-    for (int j = 0; j < 64; ++j) {
+    for (int j = 0; j < kCols; ++j) {
       const float s = (PARTIAL && j >= valid) ? kEmptyNh : v[j];
       cmax[j] = fmaxf(cmax[j], s);
     }
   } else {
 #pragma unroll
-    for (int j4 = 0; j4 < 16; ++j4) {
+    for (int j4 = 0; j4 < kCols / 4; ++j4) {
       float s4[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) s4[e] = (PARTIAL && j4 * 4 + e >= valid) ? kEmptyNh : v[j4 * 4 + e];
       const float m4 = fmaxf(fmaxf(s4[0], s4[1]), fmaxf(s4[2], s4[3]));
-      if (m4 >= thr) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (s4[e] >= thr) {
-            slots[pending * kEpiThreads] = n_first + j4 * 4 + e;
-            ++pending;
-          }
-        }
-        if (pending > kPend - 4) {  // the next group of 4 must always fit
-          flush_pending(slots, pending, p.cand, p.cand_cnt, q);
-          pending = 0;
-        }
+      if (m4 >= thr) {  // if-converted: two predicated stores and an increment
+        ps[pending * kEpiThreads] = make_float4(s4[0], s4[1], s4[2], s4[3]);
+        pp[pending * kEpiThreads] = n_first + j4 * 4;
+        ++pending;
       }
     }
   }
@@ -181,17 +219,15 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw);
-  const uint32_t q_smem = base;
-  const uint32_t stage0 = base + kTileBytes;
-  const uint32_t bars = base + kTileBytes * (1 + kStages);
+  const uint32_t stage0 = base;
+  const uint32_t bars = base + kTileBytes * kStages;
   const uint32_t bar_full = bars;                                // [kStages]
   const uint32_t bar_empty = bars + 8 * kStages;                 // [kStages]
   const uint32_t bar_acc_full = bars + 16 * kStages;             // [kAccStages]
   const uint32_t bar_acc_empty = bar_acc_full + 8 * kAccStages;  // [kAccStages]
   const uint32_t tmem_slot = bar_acc_empty + 8 * kAccStages;
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + kTileBytes * (1 + kStages) + 16 * kStages + 16 * kAccStages);
-  int32_t* pend_smem = reinterpret_cast<int32_t*>(base_ptr + kTileBytes * (1 + kStages) + kBarBytes);
+      reinterpret_cast<volatile uint32_t*>(base_ptr + kTileBytes * kStages + 16 * kStages + 16 * kAccStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x % p.n_mtiles;
@@ -207,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
     }
     for (int a = 0; a < kAccStages; ++a) {
       mbar_init(bar_acc_full + 8 * a, 1);
-      mbar_init(bar_acc_empty + 8 * a, 8);
+      mbar_init(bar_acc_empty + 8 * a, kEpiThreads / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -219,133 +255,148 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
   // The first ring of key tiles does not depend on anything below: get it in flight now.
   if (threadIdx.x == 0) {
     const int pre = n_tiles < kStages ? n_tiles : kStages;
-    for (int i = 0; i < pre; ++i) {
+    for (int i = 0; i < pre; i += 2) {  // even tiles belong to this producer (warp 0), odd ones to warp 3
       mbar_arrive_expect_tx(bar_full + 8 * i, kTileBytes);
       bulk_g2s(stage0 + i * kTileBytes, p.key_tiles + (int64_t)(t0 + i) * kTileBytes, kTileBytes, bar_full + 8 * i);
     }
-  }
-  // Query tile: 128 rows x 64 channels fp32 -> bf16, 128B-swizzled K-major, + the (1,1,1,0..) slice.
-  {
-    uint8_t* qt = base_ptr;
-    const int64_t q0 = (int64_t)m_tile * 128;
-    constexpr int kPairs = 128 * 32, kIters = (kPairs + kThreads - 1) / kThreads;
-    float va[kIters], vb[kIters];
-#pragma unroll
-    for (int it = 0; it < kIters; ++it) {  // all loads first: one memory round trip for the whole tile
-      const int e = threadIdx.x + it * kThreads;
-      const int r = e & 127, cp = e >> 7;  // channel pair cp: channels 2cp, 2cp+1
-      va[it] = 0.f;
-      vb[it] = 0.f;
-      if (e < kPairs && q0 + r < p.n_query) {
-        va[it] = __ldg(p.query + (int64_t)(2 * cp) * p.query_ch_stride + q0 + r);
-        vb[it] = __ldg(p.query + (int64_t)(2 * cp + 1) * p.query_ch_stride + q0 + r);
-      }
-    }
-#pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int e = threadIdx.x + it * kThreads;
-      const int r = e & 127, cp = e >> 7;
-      if (e < kPairs)
-        *reinterpret_cast<__nv_bfloat162*>(qt + swizzle128_offset(r, cp >> 2) + (cp & 3) * 4) =
-            __floats2bfloat162_rn(va[it], vb[it]);
-    }
-    for (int e = threadIdx.x; e < 128 * 2; e += kThreads) {
-      const int r = e >> 1, h = e & 1;
-      uint4 w = make_uint4(0, 0, 0, 0);
-      if (h == 0 && q0 + r < p.n_query) {
-        w.x = 0x3f803f80u;  // bf16 (1, 1)
-        w.y = 0x00003f80u;  // bf16 (1, 0)
-      }
-      *reinterpret_cast<uint4*>(qt + kTileKeyBytes + swizzle32_offset(r, h)) = w;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tcgen05 (async proxy)
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 0) {
-    // ===== TMA producer =====
+  // Query operand: thread r of the first epilogue warpgroup converts query row q0 + r (64 channels, read in the
+  // caller's layout, coalesced across the warp) to bf16 pairs and stores them, followed by the (1, 1, 1, 0...)
+  // slice that meets the keys' -|k|^2/2 slice, into TMEM lane r.
+  if (warp >= 4 && warp < 8) {
+    const int r = (warp - 4) * 32 + lane;
+    const int64_t qrow = (int64_t)m_tile * 128 + r;
+    const bool live = qrow < p.n_query;
+    float f[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) f[c] = live ? __ldg(p.query + (int64_t)c * p.query_ch_stride + qrow) : 0.f;
+    const uint32_t a_addr = tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + kQueryCol;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const __nv_bfloat162 v2 = __floats2bfloat162_rn(f[k * 16 + 2 * j], f[k * 16 + 2 * j + 1]);
+        w[j] = *reinterpret_cast<const uint32_t*>(&v2);
+      }
+      tmem_st8(a_addr + 8 * k, w);
+    }
+    const uint32_t aug[8] = {live ? 0x3f803f80u : 0u, live ? 0x00003f80u : 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    tmem_st8(a_addr + 32, aug);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 0 || warp == 3) {
+    // ===== TMA producers: warp 0 streams the even tiles, warp 3 the odd ones =====
     if (lane == 0) {
-      for (int i = kStages; i < n_tiles; ++i) {  // tiles [0, kStages) were issued in the prologue
+      // warp 0 already issued its tiles below kStages in the prologue
+      for (int i = (warp == 0 ? kStages : 1); i < n_tiles; i += 2) {
         const int s = i % kStages;
         const uint32_t ph = (uint32_t)((i / kStages) & 1);
         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        EVAVOS_TR(0, i);
         mbar_arrive_expect_tx(bar_full + 8 * s, kTileBytes);
         bulk_g2s(stage0 + s * kTileBytes, p.key_tiles + (int64_t)(t0 + i) * kTileBytes, kTileBytes, bar_full + 8 * s);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    const uint64_t adesc0 = make_desc(q_smem, 1024, kLayoutSw128);
-    const uint64_t adesc_aug = make_desc(q_smem + kTileKeyBytes, 256, kLayoutSw32);
+    const uint32_t a_tmem = tmem_base + kQueryCol;
     for (int i = 0; i < n_tiles; ++i) {
       const int s = i % kStages, a = i % kAccStages;
       mbar_wait(bar_full + 8 * s, (uint32_t)((i / kStages) & 1));
       mbar_wait(bar_acc_empty + 8 * a, (uint32_t)(((i / kAccStages) & 1) ^ 1));
       tc_fence_after();
       if (lane == 0) {
+        EVAVOS_TR(1, i);
         const uint32_t st = stage0 + s * kTileBytes;
         const uint64_t bdesc0 = make_desc(st, 1024, kLayoutSw128);
         const uint64_t bdesc_aug = make_desc(st + kTileKeyBytes, 256, kLayoutSw32);
         const uint32_t d = tmem_base + a * 128;
+#ifdef EVAVOS_TRACE
+        if (p.n_pos & 1) {  // trace builds only: odd n_pos = "skip the MMAs" timing experiment
+          umma_bf16_ts(d, a_tmem + 32, bdesc_aug, kInstrDesc, 0u);
+        } else
+#endif
+        {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // K = 16 bf16 = 32 B per MMA: advance 2 x 16-byte units inside the swizzle atom
-          umma_bf16(d, adesc0 + 2 * k, bdesc0 + 2 * k, kInstrDesc, k > 0 ? 1u : 0u);
-        umma_bf16(d, adesc_aug, bdesc_aug, kInstrDesc, 1u);  // += -|k|^2/2
+          for (int k = 0; k < 4; ++k)  // K = 16 bf16 = 32 B per MMA: advance 2 x 16-byte units inside the swizzle atom
+            umma_bf16_ts(d, a_tmem + 8 * k, bdesc0 + 2 * k, kInstrDesc, k > 0 ? 1u : 0u);
+          umma_bf16_ts(d, a_tmem + 32, bdesc_aug, kInstrDesc, 1u);  // += -|k|^2/2
+        }
         umma_commit(bar_empty + 8 * s);      // smem stage free once these MMAs have read it
         umma_commit(bar_acc_full + 8 * a);   // accumulator tile complete
+        EVAVOS_TR(2, i);
       }
       __syncwarp();
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> running class max / candidate append =====
+    // ===== epilogue: TMEM -> registers -> running class max / staged hit groups =====
     const int ew = warp - 4;
-    const int quarter = ew & 3;       // TMEM lane quarter this warp may access
-    const int col0 = (ew >> 2) * 64;  // accumulator columns of this warpgroup
+    const int quarter = ew & 3;           // TMEM lane quarter this warp may access
+    const int col0 = (ew >> 2) * kCols;   // accumulator columns of this warpgroup
     const int row = quarter * 32 + lane;
+    const int et = threadIdx.x - 128;
     const int64_t q = (int64_t)m_tile * 128 + row;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
 
-    float cmax[PASS == 1 ? 64 : 1];
+    float cmax[PASS == 1 ? kCols : 1];
     float thr = INFINITY;
-    int32_t* slots = pend_smem + (threadIdx.x - 128);
+    float4* ps = nullptr;
+    int32_t* pp = nullptr;
     int pending = 0;
     if constexpr (PASS == 1) {
 #pragma unroll
-      for (int j = 0; j < 64; ++j) cmax[j] = kEmptyNh;
+      for (int j = 0; j < kCols; ++j) cmax[j] = kEmptyNh;
     } else {
       if (q < p.n_query) thr = p.tau[q];
+      ps = p.pend_score + (int64_t)blockIdx.x * kPend * kEpiThreads + et;
+      pp = p.pend_pos + (int64_t)blockIdx.x * kPend * kEpiThreads + et;
     }
 
     for (int i = 0; i < n_tiles; ++i) {
       const int a = i % kAccStages;
       mbar_wait(bar_acc_full + 8 * a, (uint32_t)((i / kAccStages) & 1));
       tc_fence_after();
-      float v[64];
+      if (threadIdx.x == 128) EVAVOS_TR(3, i);
+      float v[kCols];
       tmem_ld32(lane_addr + (uint32_t)(a * 128 + col0), v);
-      tmem_ld32(lane_addr + (uint32_t)(a * 128 + col0 + 32), v + 32);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty + 8 * a);  // registers hold the tile: release the TMEM stage
+      if (threadIdx.x == 128) EVAVOS_TR(4, i);
       const int64_t n0 = (int64_t)(t0 + i) * kTilePos + col0;
-      if (n0 + 64 > p.n_pos) {
+      if (n0 + kCols > p.n_pos) {
         const int valid = (int)max((int64_t)0, p.n_pos - n0);
-        consume_tile<PASS, true>(v, cmax, thr, (int32_t)n0, valid, slots, pending, p, q);
+        consume_tile<PASS, true>(v, cmax, thr, (int32_t)n0, valid, ps, pp, pending);
       } else {
-        consume_tile<PASS, false>(v, cmax, thr, (int32_t)n0, 64, slots, pending, p, q);
+        consume_tile<PASS, false>(v, cmax, thr, (int32_t)n0, kCols, ps, pp, pending);
       }
+      if constexpr (PASS == 2) {
+        if (pending > kPend - kCols / 4) {  // the next tile stages at most kCols / 4 groups
+          flush_pending(ps, pp, pending, thr, p.cand, p.cand_cnt, q);
+          pending = 0;
+        }
+      }
+      if (threadIdx.x == 128) EVAVOS_TR(5, i);
     }
 
     if constexpr (PASS == 1) {
       float4* dst = reinterpret_cast<float4*>(p.class_max + ((int64_t)chunk * p.nq_pad + q) * 128 + col0);
 #pragma unroll
-      for (int j4 = 0; j4 < 16; ++j4)
+      for (int j4 = 0; j4 < kCols / 4; ++j4)
         dst[j4] = make_float4(cmax[j4 * 4], cmax[j4 * 4 + 1], cmax[j4 * 4 + 2], cmax[j4 * 4 + 3]);
     } else {
-      if (pending > 0) flush_pending(slots, pending, p.cand, p.cand_cnt, q);
+      if (pending > 0) flush_pending(ps, pp, pending, thr, p.cand, p.cand_cnt, q);
     }
   }
 
@@ -368,9 +419,19 @@ int score_pass_chunks(int64_t n_pos, int64_t n_query, int n_sm) {
   return (int)g;
 }
 
+#ifdef EVAVOS_TRACE
+extern "C" int evavos_debug_trace(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 6 * 64);
+}
+#endif
+
+size_t score_pass_pending_bytes(int64_t n_query, int n_chunks) {
+  return (size_t)ceil_div(n_query, 128) * n_chunks * kPend * kEpiThreads * (sizeof(float4) + sizeof(int32_t));
+}
+
 int launch_score_pass(int pass, const float* query, int64_t query_ch_stride, const void* key_tiles, int64_t n_pos,
                       int64_t n_query, int n_chunks, float* class_max, const float* tau, int32_t* cand,
-                      int32_t* cand_cnt, cudaStream_t st) {
+                      int32_t* cand_cnt, void* pending, cudaStream_t st) {
   PassParams p;
   p.query = query;
   p.query_ch_stride = query_ch_stride;
@@ -386,6 +447,9 @@ int launch_score_pass(int pass, const float* query, int64_t query_ch_stride, con
   p.cand = cand;
   p.cand_cnt = cand_cnt;
   const unsigned grid = (unsigned)(p.n_mtiles * n_chunks);
+  p.pend_score = reinterpret_cast<float4*>(pending);
+  p.pend_pos = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(pending) +
+                                          (size_t)grid * kPend * kEpiThreads * sizeof(float4));
   static bool attr_set = false;
   if (!attr_set) {
     EVAVOS_CUDA_OK(cudaFuncSetAttribute(score_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));

@@ -212,122 +212,111 @@ __global__ void __launch_bounds__(256) brute_select_kernel(
   }
 }
 
-// One warp per query: k-th largest of 128 class maxima by bitwise radix descent.
+// One 128-thread CTA per query, one thread per column class: maximum over the memory-axis chunks, then the
+// k-th largest of the 128 class maxima by all-pairs ranking in shared memory.
 __global__ void __launch_bounds__(128) threshold_kernel(
     const float* __restrict__ class_max, int n_chunks, int64_t n_query, int64_t nq_pad, int top_k,
     const float* __restrict__ query, int64_t query_ch_stride, const float* __restrict__ key_maxnorm,
     float* __restrict__ tau, int32_t* __restrict__ cand_cnt) {
-  const int lane = threadIdx.x & 31;
-  const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (q >= n_query) return;
-  float v[4] = {kEmptyNh, kEmptyNh, kEmptyNh, kEmptyNh};
-#pragma unroll 4
-  for (int g = 0; g < n_chunks; ++g) {
-    const float* row = class_max + ((int64_t)g * nq_pad + q) * 128;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) v[t] = fmaxf(v[t], __ldg(row + lane + 32 * t));
-  }
-  // |q|^2 over the 64 key channels (two per lane)
+  __shared__ unsigned long long keys[128];
+  __shared__ float warp_sq[4];
+  const int tid = threadIdx.x;
+  const int64_t q = blockIdx.x;
+  float v = kEmptyNh;
+#pragma unroll 8
+  for (int g = 0; g < n_chunks; ++g) v = fmaxf(v, __ldg(class_max + ((int64_t)g * nq_pad + q) * 128 + tid));
+  // |q|^2 over the 64 key channels
   float qsq = 0.f;
-  {
-    const float a = __ldg(query + (int64_t)lane * query_ch_stride + q);
-    const float b = __ldg(query + (int64_t)(lane + 32) * query_ch_stride + q);
-    qsq = fmaf(a, a, b * b);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) qsq += __shfl_xor_sync(0xffffffffu, qsq, o);
+  if (tid < 64) {
+    const float a = __ldg(query + (int64_t)tid * query_ch_stride + q);
+    qsq = a * a;
   }
-  uint32_t key[4];
 #pragma unroll
-  for (int t = 0; t < 4; ++t) key[t] = float_to_ordered(v[t]);
-  uint32_t pfx = 0;
-  for (int bit = 31; bit >= 0; --bit) {
-    const uint32_t trial = pfx | (1u << bit);
-    int cnt = 0;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) cnt += __popc(__ballot_sync(0xffffffffu, key[t] >= trial));
-    if (cnt >= top_k) pfx = trial;
-  }
-  if (lane == 0) {
-    const float kth = ordered_to_float(pfx);
-    const float qn = sqrtf(qsq) * 1.0001f;
+  for (int o = 16; o > 0; o >>= 1) qsq += __shfl_xor_sync(0xffffffffu, qsq, o);
+  if ((tid & 31) == 0) warp_sq[tid >> 5] = qsq;
+  const unsigned long long mine = ((unsigned long long)float_to_ordered(v) << 32) | (unsigned long long)(127 - tid);
+  keys[tid] = mine;
+  __syncthreads();
+  int rank = 0;
+#pragma unroll 8
+  for (int j = 0; j < 128; ++j) rank += keys[j] > mine ? 1 : 0;
+  if (rank == top_k - 1) {  // exactly one thread: keys are unique
+    const float qn = sqrtf(warp_sq[0] + warp_sq[1]) * 1.0001f;
     const float kn = *key_maxnorm;
     // |q^.k^ - q.k| <= 2^-8 (1 + 2^-10) |q||k| for bf16 round-to-nearest operands, plus slack for the
     // tensor-core fp32 accumulation and the rounding of -|k|^2/2.
     const float eps = 0.004f * qn * kn + 2.0e-6f * kn * kn + 1.0e-30f;
-    tau[q] = kth - 2.0f * eps;
+    tau[q] = v - 2.0f * eps;
     cand_cnt[q] = 0;
   }
 }
 
-// One warp per query, 4 warps per CTA.  Candidates are rescored exactly, ranked all-pairs
-// (rank = number of candidates with a larger (score, -position) key), and the first top_k ranks
-// are written best-first with their softmax weights.
+// One 128-thread CTA per query.  Every thread rescoring one (or two) candidates exactly, keys go to shared
+// memory, each thread ranks its candidates all-pairs (rank = number of candidates with a larger
+// (score, -position) key), and the first top_k ranks are written best-first with their softmax weights.
+// The work per query is tiny; the kernel is latency-bound, so it runs all queries at once (about 11
+// resident CTAs per SM at 480p) and keeps every candidate's row loads independent.
 __global__ void __launch_bounds__(128) finalize_kernel(
     const float* __restrict__ key_pm, const float* __restrict__ query, int64_t query_ch_stride, int CK,
     int64_t n_query, int top_k, const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
     int32_t* __restrict__ out_idx, float* __restrict__ out_weight, float* __restrict__ out_score) {
-  __shared__ __align__(16) float qs_all[4][64];
-  __shared__ unsigned long long keys_all[4][kCandCap];
-  __shared__ unsigned long long sel_all[4][EVAVOS_MAX_TOPK];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t q = (int64_t)blockIdx.x * 4 + warp;
-  if (q >= n_query) return;
-  float* qs = qs_all[warp];
-  unsigned long long* keys = keys_all[warp];
-  unsigned long long* sel = sel_all[warp];
-  for (int c = lane; c < 64; c += 32) qs[c] = (c < CK) ? __ldg(query + (int64_t)c * query_ch_stride + q) : 0.f;
-  __syncwarp();
+  __shared__ __align__(16) float qs[64];
+  __shared__ unsigned long long keys[kCandCap];
+  __shared__ unsigned long long sel[EVAVOS_MAX_TOPK];
+  __shared__ float warp_sum[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t q = blockIdx.x;
+  const int cnt = min(cand_cnt[q], kCandCap);
+  int32_t my_n[kCandCap / 128];
+#pragma unroll
+  for (int t = 0; t < kCandCap / 128; ++t) {
+    const int ci = tid + 128 * t;
+    my_n[t] = ci < cnt ? cand[q * kCandCap + ci] : -1;
+  }
+  if (tid < 64) qs[tid] = (tid < CK) ? __ldg(query + (int64_t)tid * query_ch_stride + q) : 0.f;
+  __syncthreads();
   const float qq = sumsq(qs, CK);
   const float inv_sqrt_ck = 1.0f / sqrtf((float)CK);
-  const int cnt = min(cand_cnt[q], kCandCap);
-  const int slots = (cnt + 31) >> 5;  // warp-uniform
-
-  for (int t = 0; t < slots; ++t) {
-    const int ci = lane + 32 * t;
+#pragma unroll
+  for (int t = 0; t < kCandCap / 128; ++t) {
+    const int ci = tid + 128 * t;
     unsigned long long key = 0ull;
-    if (ci < cnt) {
-      const int32_t n = cand[q * kCandCap + ci];
+    if (my_n[t] >= 0) {
       float kk, kq;
-      dot_row(reinterpret_cast<const float4*>(key_pm + (int64_t)n * CK), qs, CK, kk, kq);
+      dot_row(reinterpret_cast<const float4*>(key_pm + (int64_t)my_n[t] * CK), qs, CK, kk, kq);
       const float s = affinity_from_parts(kk, kq, qq, inv_sqrt_ck);
-      key = ((unsigned long long)float_to_ordered(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
+      key = ((unsigned long long)float_to_ordered(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)my_n[t]);
     }
     keys[ci] = key;
   }
-  __syncwarp();
+  __syncthreads();
   const int take = min(top_k, cnt);
-  for (int t = 0; t < slots; ++t) {
-    const int ci = lane + 32 * t;
-    const unsigned long long mine = keys[ci];
-    int rank = 0;
-    for (int j = 0; j < cnt; ++j) rank += keys[j] > mine ? 1 : 0;  // broadcast reads; keys are unique
-    if (ci < cnt && rank < take) sel[rank] = mine;
-  }
-  __syncwarp();
-  const float s0 = take > 0 ? ordered_to_float((uint32_t)(sel[0] >> 32)) : 0.f;
-  float e[EVAVOS_MAX_TOPK / 32];
-  float part = 0.f;
 #pragma unroll
-  for (int t = 0; t < EVAVOS_MAX_TOPK / 32; ++t) {
-    const int j = lane + 32 * t;
-    e[t] = 0.f;
-    if (j < take) {
-      e[t] = expf(ordered_to_float((uint32_t)(sel[j] >> 32)) - s0);  // exp(values - values[:,0])
-      part += e[t];
+  for (int t = 0; t < kCandCap / 128; ++t) {
+    const int ci = tid + 128 * t;
+    if (ci < cnt) {
+      const unsigned long long mine = keys[ci];
+      int rank = 0;
+      for (int j = 0; j < cnt; ++j) rank += keys[j] > mine ? 1 : 0;  // broadcast reads; keys are unique
+      if (rank < take) sel[rank] = mine;
     }
   }
+  __syncthreads();
+  const float s0 = take > 0 ? ordered_to_float((uint32_t)(sel[0] >> 32)) : 0.f;
+  float e = 0.f;
+  if (tid < take) e = expf(ordered_to_float((uint32_t)(sel[tid] >> 32)) - s0);  // exp(values - values[:,0])
+  float part = e;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-#pragma unroll
-  for (int t = 0; t < EVAVOS_MAX_TOPK / 32; ++t) {
-    const int j = lane + 32 * t;
-    if (j < top_k) {
-      const bool live = j < take;
-      const int64_t o = q * top_k + j;
-      if (out_idx) out_idx[o] = live ? (int32_t)(0xffffffffu - (uint32_t)(sel[j] & 0xffffffffull)) : -1;
-      if (out_weight) out_weight[o] = live ? e[t] / part : 0.f;
-      if (out_score) out_score[o] = live ? ordered_to_float((uint32_t)(sel[j] >> 32)) : -INFINITY;
-    }
+  if (lane == 0) warp_sum[warp] = part;
+  __syncthreads();
+  const float total = (warp_sum[0] + warp_sum[1]) + (warp_sum[2] + warp_sum[3]);
+  if (tid < top_k) {
+    const bool live = tid < take;
+    const int64_t o = q * top_k + tid;
+    if (out_idx) out_idx[o] = live ? (int32_t)(0xffffffffu - (uint32_t)(sel[tid] & 0xffffffffull)) : -1;
+    if (out_weight) out_weight[o] = live ? e / total : 0.f;
+    if (out_score) out_score[o] = live ? ordered_to_float((uint32_t)(sel[tid] >> 32)) : -INFINITY;
   }
 }
 
@@ -349,7 +338,7 @@ int launch_brute_select(const float* key_pm, const float* query, int64_t query_c
 int launch_threshold(const float* class_max, int n_chunks, int64_t n_query, int64_t nq_pad, int top_k,
                      const float* query, int64_t query_ch_stride, const float* key_maxnorm, float* tau,
                      int32_t* cand_cnt, cudaStream_t st) {
-  threshold_kernel<<<(unsigned)ceil_div(n_query, 4), 128, 0, st>>>(class_max, n_chunks, n_query, nq_pad, top_k, query,
+  threshold_kernel<<<(unsigned)n_query, 128, 0, st>>>(class_max, n_chunks, n_query, nq_pad, top_k, query,
                                                                   query_ch_stride, key_maxnorm, tau, cand_cnt);
   EVAVOS_CUDA_OK(cudaGetLastError());
   return EVAVOS_OK;
@@ -358,7 +347,7 @@ int launch_threshold(const float* class_max, int n_chunks, int64_t n_query, int6
 int launch_finalize(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_query,
                     int top_k, const int32_t* cand, const int32_t* cand_cnt, int32_t* out_idx, float* out_weight,
                     float* out_score, cudaStream_t st) {
-  finalize_kernel<<<(unsigned)ceil_div(n_query, 4), 128, 0, st>>>(key_pm, query, query_ch_stride, CK, n_query, top_k,
+  finalize_kernel<<<(unsigned)n_query, 128, 0, st>>>(key_pm, query, query_ch_stride, CK, n_query, top_k,
                                                                   cand, cand_cnt, out_idx, out_weight, out_score);
   EVAVOS_CUDA_OK(cudaGetLastError());
   return EVAVOS_OK;
