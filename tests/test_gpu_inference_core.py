@@ -1,0 +1,90 @@
+"""GPU: InferenceCore.interact end to end against the reference's outputs (seeded random weights)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import load
+
+pytestmark = pytest.mark.gpu
+
+
+def _nets():
+    import evavos_b200 as ev
+    from evavos_b200.networks import seeded_init
+    prop, fuse = ev.PropagationNetwork().eval(), ev.FusionNet().eval()
+    seeded_init(prop, 1001)
+    seeded_init(fuse, 1002)
+    return prop, fuse
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _fp32_convs():
+    # the golden vectors were produced with fp32 convolutions on the CPU; keep cuDNN out of TF32
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.set_grad_enabled(False)
+    yield
+    torch.backends.cudnn.allow_tf32 = old
+    torch.set_grad_enabled(True)
+
+
+@pytest.mark.parametrize("tag", ["e2e_k1", "e2e_k2"])
+def test_interact_matches_reference(tag):
+    import evavos_b200 as ev
+    g = load(f"{tag}.npz")
+    prop, fuse = _nets()
+    images = torch.from_numpy(g["images"])
+    k = int(g["num_objects"])
+    proc = ev.InferenceCore(prop, fuse, images, k, mem_freq=int(g["mem_freq"]), device="cuda:0")
+    assert tuple(proc.pad) == tuple(int(x) for x in g["pad"])
+    for n in range(int(g["n_interactions"])):
+        mask = torch.from_numpy(g[f"mask_{n}"])
+        out = proc.interact(mask, int(g[f"frame_{n}"]), scribble=bool(g[f"scribble_{n}"]))
+        ref_prob, ref_masks = g[f"prob_{n}"], g[f"np_masks_{n}"]
+        prob = proc.prob.cpu().numpy()
+        assert prob.shape == ref_prob.shape and out.shape == ref_masks.shape and out.dtype == np.uint8
+        # conv stacks run on different hardware (cuDNN fp32 vs MKL fp32): allow 2e-3 on probabilities
+        assert np.abs(prob - ref_prob).max() < 2e-3, np.abs(prob - ref_prob).max()
+        # masks may only differ where the reference itself is undecided (two channels within 4e-3)
+        srt = np.sort(ref_prob, 0)
+        undecided = (srt[-1] - srt[-2] < 4e-3)[:, 0]
+        lw, uw, lh, uh = (int(x) for x in g["pad"])
+        undecided = undecided[:, lh:undecided.shape[1] - uh or None, lw:undecided.shape[2] - uw or None]
+        diff = out != ref_masks
+        assert not (diff & ~undecided).any()
+        assert diff.mean() < 1e-3        # mask IoU parity gate: >= 0.999 agreement
+    # the state the callers read
+    assert proc.certain_mem_k.shape[2] == int(g["n_interactions"]) and proc.certain_mem_v.shape[0] == k
+    # policies deep-copy the processor (interactions/policies.py:103)
+    clone = copy.deepcopy(proc)
+    assert torch.equal(clone.prob, proc.prob) and clone.certain_mem_k.data_ptr() != proc.certain_mem_k.data_ptr()
+
+
+def test_reference_style_prop_net_is_accepted():
+    """A network that only offers the reference's interface (no read_memory/decode helpers) still works."""
+    import evavos_b200 as ev
+    prop, fuse = _nets()
+
+    class Foreign(torch.nn.Module):   # stands in for the reference's own PropagationNetwork class
+        def __init__(self, p):
+            super().__init__()
+            self.value_encoder, self.key_encoder, self.key_proj, self.key_comp = p.value_encoder, p.key_encoder, p.key_proj, p.key_comp
+            self.decoder, self.attn_memory = p.decoder, p.attn_memory
+            self.encode_key, self.encode_value, self.get_attention = p.encode_key, p.encode_value, p.get_attention
+
+    g = load("e2e_k1.npz")
+    images = torch.from_numpy(g["images"])
+    a = ev.InferenceCore(prop, fuse, images, 1, mem_freq=2, device="cuda:0")
+    b = ev.InferenceCore(Foreign(prop), fuse, images, 1, mem_freq=2, device="cuda:0")
+    mask = torch.from_numpy(g["mask_0"])
+    assert np.array_equal(a.interact(mask, 0), b.interact(mask, 0))
+    assert torch.equal(a.prob, b.prob)
+
+
+def test_cpu_device_rejected():
+    import evavos_b200 as ev
+    prop, fuse = _nets()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ev.InferenceCore(prop, fuse, torch.zeros(1, 2, 3, 128, 160), 1, device="cpu")
