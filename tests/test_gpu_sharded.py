@@ -1,0 +1,93 @@
+"""GPU: the merge step of the memory-axis sharded read (CUDA kernels), on one device and over NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import memread_np as onp
+from tests.helpers import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_shards_on_one_device_equal_single_bank():
+    """Both shards computed on cuda:0: local top-k -> merge kernel -> partial readouts sum to the full read."""
+    import evavos_b200 as ev
+    from evavos_b200.sharded import CudaShardOps, local_to_global
+    dev = torch.device("cuda:0")
+    K, CK, CV, T, H, W, top_k, world = 2, 64, 64, 7, 8, 10, 50, 2
+    mk, qk, mv = synth(5, CK, CV, T, H, W, K)
+    full = ev.MemoryBank.from_tensors(mk.to(dev), mv.to(dev))
+    ref, aff = ev.memory_read(full, qk.to(dev), top_k, want_topk=True)
+    ops = CudaShardOps()
+    shards = []
+    for r in range(world):
+        frames = list(range(r, T, world))
+        b = ev.MemoryBank(K, CK, CV, H, W, len(frames), dev)
+        for f in frames:
+            b.append(mk[:, :, f].to(dev), mv[:, :, f:f + 1].to(dev))
+        shards.append(b)
+    cands = []
+    for r, b in enumerate(shards):
+        idx, sc = ops.local_topk(b, qk.to(dev), top_k)
+        cands.append((local_to_global(idx, r, world, H * W), sc))
+    cand_idx = torch.cat([c[0] for c in cands], 1).contiguous()
+    cand_sc = torch.cat([c[1] for c in cands], 1).contiguous()
+    total = None
+    for r, b in enumerate(shards):
+        gidx, w, loc = ops.merge(cand_idx, cand_sc, top_k, r, world, H * W)
+        part = ops.readout(b, loc, w)
+        total = part if total is None else total + part
+        assert (gidx == aff.idx).all()
+        assert (w - aff.weight).abs().max() < 1e-6
+        owned = (loc >= 0).sum(1)
+    assert (total.view_as(ref) - ref).abs().max() < 1e-5
+    assert int(owned.max()) <= top_k
+    # against the oracle too
+    tk, ro = onp.memory_read(mk[0].reshape(CK, -1).numpy(), qk[0].reshape(CK, -1).numpy(), mv.reshape(K, CV, -1).numpy(), top_k)
+    assert onp.rel_l2(total.cpu().numpy().reshape(ro.shape), ro) < 1e-5
+
+
+def _nccl_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import evavos_b200 as ev
+        from evavos_b200.sharded import ShardedMemoryBank
+        dev = torch.device("cuda", rank)
+        K, CK, CV, T, H, W = 1, 64, 512, 9, 12, 16
+        mk, qk, mv = synth(17, CK, CV, T, H, W, K)
+        bank = ShardedMemoryBank(K, CK, CV, H, W, T, dev)
+        for f in range(T):
+            bank.append(mk[:, :, f].to(dev), mv[:, :, f:f + 1].to(dev))
+        out = bank.read(qk.to(dev), 50)
+        torch.cuda.synchronize()
+        tk, ro = onp.memory_read(mk[0].reshape(CK, -1).numpy(), qk[0].reshape(CK, -1).numpy(), mv.reshape(K, CV, -1).numpy(), 50)
+        err = onp.rel_l2(out.cpu().numpy().reshape(ro.shape), ro)
+        assert err < 1e-5, err
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_read_over_nccl():
+    import torch.multiprocessing as mp
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert all(ret.get(r) for r in range(world))
