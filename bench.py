@@ -16,6 +16,8 @@ Workload (BASELINE.json configs[1]): DAVIS-17 480p, 30x54 feature map, 3 objects
             torch path; /root/reference is not on the GPU box) on all host cores.
 Multi-GPU (torchrun, one rank per GPU): independent videos are partitioned across ranks with no
 collective -> weak scaling; value = N * K / max-over-ranks time.
+`--workload cfg4` is the long-video case instead: ONE 200-frame bank sharded along the memory axis over
+the ranks (NCCL all-gather of top-k candidates + all-reduce of partial readouts) -> strong scaling.
 """
 from __future__ import annotations
 
@@ -40,6 +42,7 @@ WORKLOADS = {
 }
 TOP_K = 50
 N_BANKS = 4
+FRAMES_PER_EXCHANGE = 5   # query frames between two memory appends (mem_freq) read in one sharded exchange
 KERNELS_PER_STEP = 9  # query shadow, pass1, threshold, pass2, overflow list, exact select, finalize, readout, aggregate
 
 
@@ -143,6 +146,88 @@ def run_reference(args, cfg, rank, world):
         "e2e": {"value": rate, "unit": "query-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def run_sharded(args, cfg, rank, world, local_rank):
+    """cfg4: one long bank sharded by frame over the ranks; strong scaling (total work fixed)."""
+    import evavos_b200 as ev
+    from evavos_b200.sharded import ShardedMemoryBank
+    ck, cv, t, h, w, k, seed, desc = cfg
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    hw, n_pos = h * w, t * h * w
+    n_banks = 2
+    banks, queries = [], []
+    for b in range(n_banks):
+        g = torch.Generator().manual_seed(seed + 100 * b)
+        bank = ShardedMemoryBank(k, ck, cv, h, w, t, dev)
+        for f in range(t):                      # same frames on every rank; only the owner keeps one
+            kf = torch.randn(1, ck, h, w, generator=g)
+            vf = torch.randn(k, cv, 1, h, w, generator=g)
+            if bank.owner_of(f) == rank:
+                bank.append(kf.to(dev), vf.to(dev))
+            else:
+                bank.n_frames += 1
+        banks.append(bank)
+        queries.append(torch.randn(1, ck, FRAMES_PER_EXCHANGE, h, w, generator=g).to(dev))
+    prob = torch.rand(k, 1, h * 16, w * 16, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i):
+        # mem_freq = 5 query frames share one bank state (inference_core.py:174): one exchange for all of them
+        out = banks[i % n_banks].read(queries[i % n_banks], TOP_K)
+        aggs = [ev.aggregate_wbg(prob, keep_bg=True) for _ in range(FRAMES_PER_EXCHANGE)]
+        return out, aggs
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize(dev)
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize(dev)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    t1.record(stream)
+    torch.cuda.synchronize(dev)
+    if dist:
+        dist.barrier()
+    elapsed_ms = t0.elapsed_time(t1)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist:
+        tm = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tm.item())
+    if rank == 0:
+        value = FRAMES_PER_EXCHANGE * args.steps / (elapsed_ms * 1e-3)
+        flops = 2.0 * n_pos * hw * ck * FRAMES_PER_EXCHANGE                       # the one unavoidable dense contraction (SURVEY.md 8d)
+        t_tc = flops / 1390.2e12
+        line = {
+            "metric": "memory-read query-frames/sec", "value": value, "unit": "query-frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + desc + f", memory axis sharded by frame over {world} GPU(s)",
+                       "top_k": TOP_K, "memory_positions": n_pos, "queries_per_frame": hw, "objects": k,
+                       "query_frames_per_step": FRAMES_PER_EXCHANGE,
+                       "l2": f"{n_banks} rotating banks, {n_banks * 4 * (k * cv + ck) * n_pos / 1e6:.0f} MB of inputs > 126 MB L2",
+                       "parallelism": f"memory-axis shards x{world}, all-gather(top-k) + all-reduce(readout)"},
+            "clocks": clocks, "gpu_launches": (KERNELS_PER_STEP + 1) * args.steps,
+            "roofline": {"bound": "tensor", "kernel": "whole sharded read (score filter dominates)", "achieved": flops / (elapsed_ms / args.steps * 1e-3) / 1e12 / world,
+                         "peak": 1390.2, "unit": "TFLOP/s", "frac": t_tc / world / (elapsed_ms / args.steps * 1e-3), "traffic": None,
+                         "note": "algorithmic flops 2*N*HW*CK per query frame over the measured step time, per GPU"},
+        }
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
 
 
 def run_ours(args, cfg, rank, world, local_rank):
@@ -311,6 +396,8 @@ def main():
     cfg = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, cfg, rank, world)
+    elif args.workload == "cfg4":
+        run_sharded(args, cfg, rank, world, local_rank)
     else:
         run_ours(args, cfg, rank, world, local_rank)
 

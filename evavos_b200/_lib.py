@@ -62,6 +62,8 @@ SIGNATURES = {
     "evavos_aggregate_wbg": (_c_i32, [_c_vp, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_vp]),
     "evavos_topk_merge": (_c_i32, [_c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_i32, _c_i32, _c_i64, _c_vp, _c_vp, _c_vp,
                                    _c_vp, _c_vp]),
+    "evavos_topk_merge_gathered": (_c_i32, [_c_vp, _c_i64, _c_i32, _c_i32, _c_i32, _c_i32, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp,
+                                            _c_vp]),
     "evavos_memread_host": (_c_i32, [_c_vp, _c_vp, _c_vp, _c_i32, _c_i32, _c_i32, _c_i64, _c_i64, _c_i32, _c_i32,
                                      _c_vp, _c_vp, _c_vp, ctypes.POINTER(_c_i64), ctypes.POINTER(_c_i64)]),
     "evavos_release_host_scratch": (_c_i32, []),

@@ -269,7 +269,19 @@ int evavos_topk_merge(const int32_t* cand_idx, const float* cand_score, int64_t 
     return EVAVOS_ERR_INVALID;
   }
   return launch_topk_merge(cand_idx, cand_score, n_query, n_cand, top_k, shard, n_shards, pos_per_frame, out_idx,
-                           out_weight, out_score, local_idx, (cudaStream_t)stream);
+                           out_weight, out_score, local_idx, 0, (cudaStream_t)stream);
+}
+
+int evavos_topk_merge_gathered(const int32_t* gathered, int64_t n_query, int32_t per_shard, int32_t top_k,
+                               int32_t shard, int32_t n_shards, int64_t pos_per_frame, int32_t* out_idx,
+                               float* out_weight, float* out_score, int32_t* local_idx, evavos_stream_t stream) {
+  if (!gathered || n_query <= 0 || per_shard <= 0 || top_k <= 0 || top_k > EVAVOS_MAX_TOPK || n_shards <= 0 ||
+      shard < 0 || shard >= n_shards || pos_per_frame <= 0) {
+    set_error("topk_merge_gathered: bad arguments");
+    return EVAVOS_ERR_INVALID;
+  }
+  return launch_topk_merge(gathered, nullptr, n_query, per_shard * n_shards, top_k, shard, n_shards, pos_per_frame,
+                           out_idx, out_weight, out_score, local_idx, 1, (cudaStream_t)stream);
 }
 
 // ---- host-buffer form ---------------------------------------------------------------------

@@ -105,6 +105,6 @@ int launch_aggregate(const float* prob, float* out, int K, int64_t npix, int kee
                      cudaStream_t st);
 int launch_topk_merge(const int32_t* cand_idx, const float* cand_score, int64_t n_query, int n_cand, int top_k,
                       int shard, int n_shards, int64_t pos_per_frame, int32_t* out_idx, float* out_weight,
-                      float* out_score, int32_t* local_idx, cudaStream_t st);
+                      float* out_score, int32_t* local_idx, int gathered, cudaStream_t st);
 
 }  // namespace evavos

@@ -12,6 +12,11 @@ namespace evavos {
 
 namespace {
 
+// GATHERED = false: cand_idx / cand_score are (n_query, n_cand) with GLOBAL positions.
+// GATHERED = true : cand_idx is the raw all-gather output [n_shards][n_query][per_shard][2] of packed
+//                   (LOCAL position, score bits) pairs, n_cand = n_shards * per_shard; the position of entry c
+//                   comes from shard c / per_shard and is mapped to its global position here.
+template <bool GATHERED>
 __global__ void __launch_bounds__(128) topk_merge_kernel(
     const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_score, int64_t n_query, int n_cand,
     int top_k, int shard, int n_shards, int64_t pos_per_frame, int32_t* __restrict__ out_idx,
@@ -23,12 +28,27 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(
   unsigned long long* keys = smem_keys + (size_t)warp * n_cand;
   unsigned long long* sel = smem_keys + (size_t)4 * n_cand + (size_t)warp * EVAVOS_MAX_TOPK;
   int live = 0;
+  const int per_shard = n_cand / n_shards;
   for (int c = lane; c < n_cand; c += 32) {
-    const int32_t n = cand_idx[q * n_cand + c];
+    int64_t n;
+    float sc;
+    if constexpr (GATHERED) {
+      const int src = c / per_shard, j = c - src * per_shard;
+      const int32_t* e = cand_idx + (((int64_t)src * n_query + q) * per_shard + j) * 2;
+      const int32_t loc = e[0];
+      sc = __int_as_float(e[1]);
+      n = -1;
+      if (loc >= 0) {
+        const int64_t frame = loc / pos_per_frame, r = loc - frame * pos_per_frame;
+        n = (frame * n_shards + src) * pos_per_frame + r;
+      }
+    } else {
+      n = cand_idx[q * n_cand + c];
+      sc = cand_score[q * n_cand + c];
+    }
     unsigned long long k = 0ull;
     if (n >= 0) {
-      k = ((unsigned long long)float_to_ordered(cand_score[q * n_cand + c]) << 32) |
-          (unsigned long long)(0xffffffffu - (uint32_t)n);
+      k = ((unsigned long long)float_to_ordered(sc) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
       ++live;
     }
     keys[c] = k;
@@ -89,18 +109,24 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(
 
 int launch_topk_merge(const int32_t* cand_idx, const float* cand_score, int64_t n_query, int n_cand, int top_k,
                       int shard, int n_shards, int64_t pos_per_frame, int32_t* out_idx, float* out_weight,
-                      float* out_score, int32_t* local_idx, cudaStream_t st) {
+                      float* out_score, int32_t* local_idx, int gathered, cudaStream_t st) {
   if (n_query <= 0) return EVAVOS_OK;
   const size_t smem = sizeof(unsigned long long) * ((size_t)4 * n_cand + 4 * EVAVOS_MAX_TOPK);
   if (smem > 200 * 1024) {
     set_error("topk_merge: n_cand=%d too large", n_cand);
     return EVAVOS_ERR_UNSUPPORTED;
   }
-  if (smem > 48 * 1024)
-    EVAVOS_CUDA_OK(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  topk_merge_kernel<<<(unsigned)ceil_div(n_query, 4), 128, smem, st>>>(cand_idx, cand_score, n_query, n_cand, top_k,
-                                                                       shard, n_shards, pos_per_frame, out_idx,
-                                                                       out_weight, out_score, local_idx);
+  if (smem > 48 * 1024) {
+    EVAVOS_CUDA_OK(cudaFuncSetAttribute(topk_merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EVAVOS_CUDA_OK(cudaFuncSetAttribute(topk_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  const unsigned grid = (unsigned)ceil_div(n_query, 4);
+  if (gathered)
+    topk_merge_kernel<true><<<grid, 128, smem, st>>>(cand_idx, cand_score, n_query, n_cand, top_k, shard, n_shards,
+                                                     pos_per_frame, out_idx, out_weight, out_score, local_idx);
+  else
+    topk_merge_kernel<false><<<grid, 128, smem, st>>>(cand_idx, cand_score, n_query, n_cand, top_k, shard, n_shards,
+                                                      pos_per_frame, out_idx, out_weight, out_score, local_idx);
   EVAVOS_CUDA_OK(cudaGetLastError());
   return EVAVOS_OK;
 }

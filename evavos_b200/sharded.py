@@ -48,6 +48,20 @@ class CudaShardOps:
                                              local_idx.data_ptr(), _lib.current_stream_ptr(dev)))
         return out_idx, weight, local_idx
 
+    def merge_gathered(self, gathered, top_k, rank, world, pos_per_frame):
+        """gathered: (world, nq, per_shard, 2) int32 = all-gather of packed (local position, score bits)."""
+        lib = _lib.load()
+        _, nq, per_shard, _ = gathered.shape
+        dev = gathered.device
+        out_idx = torch.empty((nq, top_k), dtype=torch.int32, device=dev)
+        weight = torch.empty((nq, top_k), dtype=torch.float32, device=dev)
+        local_idx = torch.empty((nq, top_k), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.evavos_topk_merge_gathered(gathered.data_ptr(), nq, per_shard, top_k, rank, world,
+                                                      pos_per_frame, out_idx.data_ptr(), weight.data_ptr(), None,
+                                                      local_idx.data_ptr(), _lib.current_stream_ptr(dev)))
+        return out_idx, weight, local_idx
+
     def readout(self, bank: MemoryBank, local_idx, weight):
         lib = _lib.load()
         nq, k = local_idx.shape
@@ -102,6 +116,9 @@ class ShardedMemoryBank:
             raise RuntimeError(f"selected index k out of range (THW={self.n_pos} < top_k={top_k})")
         spatial = tuple(qk.shape[2:])
         ops, rank, world = self.ops, self.rank, self.world
+        if world == 1 and isinstance(ops, CudaShardOps) and not return_topk:
+            out, _ = memory_read(self.local, qk, top_k)      # nothing to exchange: the ordinary fused read
+            return out
         if self.local.n_pos > 0:
             idx_loc, score = ops.local_topk(self.local, qk, top_k)
             nq, k_loc = idx_loc.shape
@@ -113,6 +130,16 @@ class ShardedMemoryBank:
             nq = int(torch.tensor(qk.shape[2:]).prod())
             idx_loc = torch.full((nq, top_k), -1, dtype=torch.int32, device=qk.device)
             score = torch.full((nq, top_k), float("-inf"), dtype=torch.float32, device=qk.device)
+        if hasattr(ops, "merge_gathered"):
+            # one collective: packed (local position, score bits) pairs; the kernel maps them to global positions
+            packed = torch.stack([idx_loc, score.view(torch.int32)], -1).contiguous()
+            if world > 1:
+                gathered = torch.empty((world,) + tuple(packed.shape), dtype=torch.int32, device=packed.device)
+                dist.all_gather_into_tensor(gathered, packed, group=self.group)
+            else:
+                gathered = packed.unsqueeze(0)
+            glob_idx, weight, local_idx = ops.merge_gathered(gathered, top_k, rank, world, self.HW)
+            return self._finish(qk, spatial, nq, glob_idx, weight, local_idx, return_topk)
         idx_glob = local_to_global(idx_loc, rank, world, self.HW).contiguous()
         score = score.contiguous()
         if world > 1:
@@ -125,6 +152,10 @@ class ShardedMemoryBank:
         else:
             cand_idx, cand_score = idx_glob, score
         glob_idx, weight, local_idx = ops.merge(cand_idx, cand_score, top_k, rank, world, self.HW)
+        return self._finish(qk, spatial, nq, glob_idx, weight, local_idx, return_topk)
+
+    def _finish(self, qk, spatial, nq, glob_idx, weight, local_idx, return_topk):
+        ops, world = self.ops, self.world
         if self.local.n_pos > 0:
             part = ops.readout(self.local, local_idx, weight)
         else:

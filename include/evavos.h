@@ -177,6 +177,15 @@ int evavos_topk_merge(const int32_t* cand_idx, const float* cand_score, int64_t 
                       evavos_stream_t stream);
 
 /*
+ * Same merge, fed directly with the all-gather output: gathered is [n_shards][n_query][per_shard][2] int32
+ * pairs of (LOCAL position on the source shard or -1, score bits).  The local -> global mapping under the
+ * round-robin frame distribution is done inside the kernel.
+ */
+int evavos_topk_merge_gathered(const int32_t* gathered, int64_t n_query, int32_t per_shard, int32_t top_k,
+                               int32_t shard, int32_t n_shards, int64_t pos_per_frame, int32_t* out_idx,
+                               float* out_weight, float* out_score, int32_t* local_idx, evavos_stream_t stream);
+
+/*
  * Host-buffer form of the read, reference layouts, synchronous:
  *   mem_key (CK, n_pos) fp32 contiguous, query (CK, n_query), mem_value (K, CV, n_pos),
  *   readout (K, CV, n_query); topk_idx/topk_weight optional (n_query, top_k).

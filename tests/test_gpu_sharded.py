@@ -45,6 +45,16 @@ def test_two_shards_on_one_device_equal_single_bank():
         owned = (loc >= 0).sum(1)
     assert (total.view_as(ref) - ref).abs().max() < 1e-5
     assert int(owned.max()) <= top_k
+    # the packed all-gather layout [shard][query][k][2] gives the same merge
+    packed = torch.stack([torch.stack([ops.local_topk(b, qk.to(dev), top_k)[0],
+                                       ops.local_topk(b, qk.to(dev), top_k)[1].view(torch.int32)], -1) for b in shards], 0)
+    total2 = None
+    for r, b in enumerate(shards):
+        gidx2, w2, loc2 = ops.merge_gathered(packed.contiguous(), top_k, r, world, H * W)
+        assert (gidx2 == aff.idx).all() and (w2 - aff.weight).abs().max() < 1e-6
+        part = ops.readout(b, loc2, w2)
+        total2 = part if total2 is None else total2 + part
+    assert torch.equal(total2, total)
     # against the oracle too
     tk, ro = onp.memory_read(mk[0].reshape(CK, -1).numpy(), qk[0].reshape(CK, -1).numpy(), mv.reshape(K, CV, -1).numpy(), top_k)
     assert onp.rel_l2(total.cpu().numpy().reshape(ro.shape), ro) < 1e-5
