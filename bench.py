@@ -43,7 +43,7 @@ WORKLOADS = {
 TOP_K = 50
 N_BANKS = 4
 FRAMES_PER_EXCHANGE = 5   # query frames between two memory appends (mem_freq) read in one sharded exchange
-KERNELS_PER_STEP = 9  # query shadow, pass1, threshold, pass2, overflow list, exact select, finalize, readout, aggregate
+KERNELS_PER_STEP = 7  # pass 1, threshold, pass 2, exact-select (overflow), finalize, readout, aggregate
 
 
 def synth(seed, ck, cv, t, h, w, k):
@@ -220,7 +220,7 @@ def run_sharded(args, cfg, rank, world, local_rank):
                        "query_frames_per_step": FRAMES_PER_EXCHANGE,
                        "l2": f"{n_banks} rotating banks, {n_banks * 4 * (k * cv + ck) * n_pos / 1e6:.0f} MB of inputs > 126 MB L2",
                        "parallelism": f"memory-axis shards x{world}, all-gather(top-k) + all-reduce(readout)"},
-            "clocks": clocks, "gpu_launches": (KERNELS_PER_STEP + 1) * args.steps,
+            "clocks": clocks, "gpu_launches": (KERNELS_PER_STEP + 1 + FRAMES_PER_EXCHANGE - 1) * args.steps,
             "roofline": {"bound": "tensor", "kernel": "whole sharded read (score filter dominates)", "achieved": flops / (elapsed_ms / args.steps * 1e-3) / 1e12 / world,
                          "peak": 1390.2, "unit": "TFLOP/s", "frac": t_tc / world / (elapsed_ms / args.steps * 1e-3), "traffic": None,
                          "note": "algorithmic flops 2*N*HW*CK per query frame over the measured step time, per GPU"},
