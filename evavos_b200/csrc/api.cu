@@ -71,6 +71,7 @@ Carve carve_workspace(const EvavosMemReadArgs& a, int n_chunks, uint8_t* base) {
   c.sb.cand_cnt = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * nq_pad));
   c.sb.cand = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * nq_pad * kCandCap));
   c.sb.pending = take(n_chunks > 0 ? score_pass_pending_bytes(a.n_query, n_chunks) : 0);
+  c.sb.grid_counter = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int)));
   c.idx = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * a.n_query * a.top_k));
   c.weight = reinterpret_cast<float*>(take(sizeof(float) * a.n_query * a.top_k));
   c.total = off + 1024;  // slack for aligning the caller's pointer
@@ -191,18 +192,11 @@ int evavos_memread(const EvavosMemReadArgs* a, evavos_stream_t stream) {
   const Carve c = carve_workspace(*a, chunks, base);
   const int CK = a->bank.CK;
 
-  const int64_t nq_pad = ceil_div(a->n_query, 128) * 128;
-
   // 1. candidate generation (the query is consumed in the caller's layout; no query shadow)
   if (tensor) {
-    rc = launch_score_pass(1, a->query, a->query_ch_stride, a->bank.key_tiles, a->n_pos, a->n_query, chunks,
-                           c.sb.class_max, nullptr, nullptr, nullptr, nullptr, st);
-    if (rc) return rc;
-    rc = launch_threshold(c.sb.class_max, chunks, a->n_query, nq_pad, a->top_k, a->query, a->query_ch_stride,
-                          a->bank.key_maxnorm, c.sb.tau, c.sb.cand_cnt, st);
-    if (rc) return rc;
-    rc = launch_score_pass(2, a->query, a->query_ch_stride, a->bank.key_tiles, a->n_pos, a->n_query, chunks, nullptr,
-                           c.sb.tau, c.sb.cand, c.sb.cand_cnt, c.sb.pending, st);
+    rc = launch_score_select(a->query, a->query_ch_stride, a->bank.key_tiles, a->bank.key_maxnorm, a->n_pos, a->n_query,
+                             a->top_k, chunks, n_sm, c.sb.class_max, c.sb.tau, c.sb.cand, c.sb.cand_cnt, c.sb.pending,
+                             c.sb.grid_counter, st);
     if (rc) return rc;
     // queries whose candidate list overflowed (massive ties) are redone exactly
     rc = launch_brute_select(a->bank.key_pm, a->query, a->query_ch_stride, CK, a->n_pos, a->n_query, a->top_k, 1,

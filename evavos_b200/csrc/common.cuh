@@ -77,7 +77,8 @@ struct SelectBuffers {
   float* tau;         // [nq_pad]
   int32_t* cand_cnt;  // [nq_pad]
   int32_t* cand;      // [nq_pad][kCandCap]
-  void* pending;      // pass-2 staging strips (score_pass_pending_bytes)
+  void* pending;      // sweep-2 staging strips (score_pass_pending_bytes)
+  unsigned int* grid_counter;
 };
 
 // The query is always addressed in the caller's layout: element (c, q) at query[c * query_ch_stride + q].
@@ -88,12 +89,9 @@ int launch_brute_select(const float* key_pm, const float* query, int64_t query_c
 int launch_finalize(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_query,
                     int top_k, const int32_t* cand, const int32_t* cand_cnt, int32_t* out_idx, float* out_weight,
                     float* out_score, cudaStream_t st);
-int launch_threshold(const float* class_max, int n_chunks, int64_t n_query, int64_t nq_pad, int top_k,
-                     const float* query, int64_t query_ch_stride, const float* key_maxnorm, float* tau,
-                     int32_t* cand_cnt, cudaStream_t st);
-int launch_score_pass(int pass, const float* query, int64_t query_ch_stride, const void* key_tiles, int64_t n_pos,
-                      int64_t n_query, int n_chunks, float* class_max, const float* tau, int32_t* cand,
-                      int32_t* cand_cnt, void* pending, cudaStream_t st);
+int launch_score_select(const float* query, int64_t query_ch_stride, const void* key_tiles, const float* key_maxnorm,
+                        int64_t n_pos, int64_t n_query, int top_k, int n_chunks, int n_sm, float* class_max, float* tau,
+                        int32_t* cand, int32_t* cand_cnt, void* pending, unsigned int* grid_counter, cudaStream_t st);
 size_t score_pass_pending_bytes(int64_t n_query, int n_chunks);
 int score_pass_chunks(int64_t n_pos, int64_t n_query, int n_sm);
 

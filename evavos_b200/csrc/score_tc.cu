@@ -8,12 +8,14 @@
 // the SM: each 128x128 accumulator tile is consumed out of TMEM and only O(k) numbers per query
 // reach HBM.
 //
-//   pass 1: running maximum of S' per (query, column class n mod 128) -> class_max.
-//           The k-th largest of a query's 128 class maxima is a lower bound on its k-th best
-//           score (k distinct positions reach it); threshold_kernel finds it.
-//   pass 2: same contraction; every position with S' >= tau_q (bound minus a rigorous bf16
-//           error margin) is appended to the query's candidate list, which therefore
-//           contains the exact fp32 top-k.  finalize_kernel's exact rescoring picks it.
+//   sweep 1: running maximum of S' per (query, column class n mod 128) -> class_max.
+//            The k-th largest of a query's 128 class maxima is a lower bound on its k-th best
+//            score (k distinct positions reach it); the CTAs agree on it across the grid.
+//   sweep 2: same contraction; every position with S' >= tau_q (bound minus a rigorous bf16
+//            error margin) is appended to the query's candidate list, which therefore
+//            contains the exact fp32 top-k.  finalize_kernel's exact rescoring picks it.
+// Both sweeps run inside ONE cooperative launch (score_select_kernel): the TMA and MMA warps simply stream the
+// chunk's tiles twice and run ahead into sweep 2 while the epilogue warps exchange thresholds.
 //
 // Roles per CTA (640 threads, 1 CTA/SM, one wave): warps 0 and 3 = TMA producers (cp.async.bulk of
 // pre-swizzled 20 KB key tile images; one issuing thread sustains only ~50 B/clk, two reach the L2
@@ -153,11 +155,15 @@ struct PassParams {
   int n_ktiles;
   int n_chunks;
   float* class_max;
-  const float* tau;
+  float* tau;
   int32_t* cand;
   int32_t* cand_cnt;
   float4* pend_score;   // [grid][kPend][kEpiThreads] scores of staged hit groups (pass 2)
   int32_t* pend_pos;    // [grid][kPend][kEpiThreads] first position of each staged group
+  const float* key_maxnorm;
+  unsigned int* grid_counter;  // zeroed before every launch
+  int m_tile0;          // first query tile of this launch
+  int top_k;
 };
 
 // Pass 2 stages every group of 4 adjacent scores whose maximum reaches the threshold (scores + first
@@ -213,8 +219,63 @@ __device__ __forceinline__ void consume_tile(const float* v, float* cmax, float 
   }
 }
 
-template <int PASS>
-__global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParams p) {
+// Grid-wide barrier among the epilogue threads of all CTAs (the grid is launched cooperatively, so every
+// CTA is resident).  `counter` only grows: the n-th barrier waits for n * gridDim.x arrivals.
+__device__ __forceinline__ void epilogue_grid_barrier(unsigned int* counter, unsigned int target) {
+  asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+  if (threadIdx.x == 128) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      if (seen < target) __nanosleep(64);
+    } while (seen < target);
+    __threadfence();
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+}
+
+// Admission threshold of one query (one warp): k-th largest of its 128 class maxima (4 per lane, maximum over the
+// memory-axis chunks) by a 32-step radix descent on order-preserving keys, minus the bf16 error margin.
+__device__ __forceinline__ void warp_threshold(const PassParams& p, int64_t q, int lane) {
+  float v[4] = {kEmptyNh, kEmptyNh, kEmptyNh, kEmptyNh};
+  for (int g = 0; g < p.n_chunks; ++g) {
+    const float* row = p.class_max + ((int64_t)g * p.nq_pad + q) * 128;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v[t] = fmaxf(v[t], __ldcg(row + lane + 32 * t));  // written by other CTAs: bypass L1
+  }
+  const float qa = __ldg(p.query + (int64_t)lane * p.query_ch_stride + q);
+  const float qb = __ldg(p.query + (int64_t)(lane + 32) * p.query_ch_stride + q);
+  float qsq = fmaf(qa, qa, qb * qb);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) qsq += __shfl_xor_sync(0xffffffffu, qsq, o);
+  uint32_t key[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) key[t] = float_to_ordered(v[t]);
+  uint32_t pfx = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t trial = pfx | (1u << bit);
+    int cnt = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) cnt += __popc(__ballot_sync(0xffffffffu, key[t] >= trial));
+    if (cnt >= p.top_k) pfx = trial;
+  }
+  if (lane == 0) {
+    const float qn = sqrtf(qsq) * 1.0001f;
+    const float kn = *p.key_maxnorm;
+    // |q^.k^ - q.k| <= 2^-8 (1 + 2^-10) |q||k| for bf16 round-to-nearest operands, plus slack for the
+    // tensor-core fp32 accumulation and the rounding of -|k|^2/2.
+    const float eps = 0.004f * qn * kn + 2.0e-6f * kn * kn + 1.0e-30f;
+    p.tau[q] = ordered_to_float(pfx) - 2.0f * eps;
+    p.cand_cnt[q] = 0;
+  }
+}
+
+// One persistent CTA per (query tile, memory chunk).  The producer and MMA warps stream the chunk's key tiles
+// twice; the epilogue warps take running class maxima on the first sweep, agree on per-query thresholds across
+// the grid, and collect candidates on the second sweep.
+__global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -230,11 +291,13 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
       reinterpret_cast<volatile uint32_t*>(base_ptr + kTileBytes * kStages + 16 * kStages + 16 * kAccStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tile = blockIdx.x % p.n_mtiles;
+  const int m_tile = p.m_tile0 + blockIdx.x % p.n_mtiles;
   const int chunk = blockIdx.x / p.n_mtiles;
   const int t0 = (int)(((int64_t)chunk * p.n_ktiles) / p.n_chunks);
   const int t1 = (int)(((int64_t)(chunk + 1) * p.n_ktiles) / p.n_chunks);
   const int n_tiles = t1 - t0;
+  const int n_iter = 2 * n_tiles;  // every key tile is contracted twice
+  auto tile_of = [&](int i) { return t0 + (i >= n_tiles ? i - n_tiles : i); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -254,10 +317,10 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
   }
   // The first ring of key tiles does not depend on anything below: get it in flight now.
   if (threadIdx.x == 0) {
-    const int pre = n_tiles < kStages ? n_tiles : kStages;
-    for (int i = 0; i < pre; i += 2) {  // even tiles belong to this producer (warp 0), odd ones to warp 3
+    const int pre = n_iter < kStages ? n_iter : kStages;
+    for (int i = 0; i < pre; i += 2) {  // even iterations belong to this producer (warp 0), odd ones to warp 3
       mbar_arrive_expect_tx(bar_full + 8 * i, kTileBytes);
-      bulk_g2s(stage0 + i * kTileBytes, p.key_tiles + (int64_t)(t0 + i) * kTileBytes, kTileBytes, bar_full + 8 * i);
+      bulk_g2s(stage0 + i * kTileBytes, p.key_tiles + (int64_t)tile_of(i) * kTileBytes, kTileBytes, bar_full + 8 * i);
     }
   }
   tc_fence_before();
@@ -295,22 +358,22 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
   tc_fence_after();
 
   if (warp == 0 || warp == 3) {
-    // ===== TMA producers: warp 0 streams the even tiles, warp 3 the odd ones =====
+    // ===== TMA producers: warp 0 streams the even iterations, warp 3 the odd ones =====
     if (lane == 0) {
-      // warp 0 already issued its tiles below kStages in the prologue
-      for (int i = (warp == 0 ? kStages : 1); i < n_tiles; i += 2) {
+      // warp 0 already issued its iterations below kStages in the prologue
+      for (int i = (warp == 0 ? kStages : 1); i < n_iter; i += 2) {
         const int s = i % kStages;
         const uint32_t ph = (uint32_t)((i / kStages) & 1);
         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
         EVAVOS_TR(0, i);
         mbar_arrive_expect_tx(bar_full + 8 * s, kTileBytes);
-        bulk_g2s(stage0 + s * kTileBytes, p.key_tiles + (int64_t)(t0 + i) * kTileBytes, kTileBytes, bar_full + 8 * s);
+        bulk_g2s(stage0 + s * kTileBytes, p.key_tiles + (int64_t)tile_of(i) * kTileBytes, kTileBytes, bar_full + 8 * s);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const uint32_t a_tmem = tmem_base + kQueryCol;
-    for (int i = 0; i < n_tiles; ++i) {
+    for (int i = 0; i < n_iter; ++i) {
       const int s = i % kStages, a = i % kAccStages;
       mbar_wait(bar_full + 8 * s, (uint32_t)((i / kStages) & 1));
       mbar_wait(bar_acc_empty + 8 * a, (uint32_t)(((i / kAccStages) & 1) ^ 1));
@@ -321,17 +384,10 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
         const uint64_t bdesc0 = make_desc(st, 1024, kLayoutSw128);
         const uint64_t bdesc_aug = make_desc(st + kTileKeyBytes, 256, kLayoutSw32);
         const uint32_t d = tmem_base + a * 128;
-#ifdef EVAVOS_TRACE
-        if (p.n_pos & 1) {  // trace builds only: odd n_pos = "skip the MMAs" timing experiment
-          umma_bf16_ts(d, a_tmem + 32, bdesc_aug, kInstrDesc, 0u);
-        } else
-#endif
-        {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // K = 16 bf16 = 32 B per MMA: advance 2 x 16-byte units inside the swizzle atom
-            umma_bf16_ts(d, a_tmem + 8 * k, bdesc0 + 2 * k, kInstrDesc, k > 0 ? 1u : 0u);
-          umma_bf16_ts(d, a_tmem + 32, bdesc_aug, kInstrDesc, 1u);  // += -|k|^2/2
-        }
+        for (int k = 0; k < 4; ++k)  // K = 16 bf16 = 32 B per MMA: advance 2 x 16-byte units inside the swizzle atom
+          umma_bf16_ts(d, a_tmem + 8 * k, bdesc0 + 2 * k, kInstrDesc, k > 0 ? 1u : 0u);
+        umma_bf16_ts(d, a_tmem + 32, bdesc_aug, kInstrDesc, 1u);  // += -|k|^2/2
         umma_commit(bar_empty + 8 * s);      // smem stage free once these MMAs have read it
         umma_commit(bar_acc_full + 8 * a);   // accumulator tile complete
         EVAVOS_TR(2, i);
@@ -339,7 +395,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
       __syncwarp();
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> running class max / staged hit groups =====
+    // ===== epilogue: TMEM -> registers -> running class max (sweep 1) / staged hit groups (sweep 2) =====
     const int ew = warp - 4;
     const int quarter = ew & 3;           // TMEM lane quarter this warp may access
     const int col0 = (ew >> 2) * kCols;   // accumulator columns of this warpgroup
@@ -348,54 +404,78 @@ __global__ void __launch_bounds__(kThreads, 1) score_pass_kernel(const PassParam
     const int64_t q = (int64_t)m_tile * 128 + row;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
 
-    float cmax[PASS == 1 ? kCols : 1];
-    float thr = INFINITY;
-    float4* ps = nullptr;
-    int32_t* pp = nullptr;
-    int pending = 0;
-    if constexpr (PASS == 1) {
-#pragma unroll
-      for (int j = 0; j < kCols; ++j) cmax[j] = kEmptyNh;
-    } else {
-      if (q < p.n_query) thr = p.tau[q];
-      ps = p.pend_score + (int64_t)blockIdx.x * kPend * kEpiThreads + et;
-      pp = p.pend_pos + (int64_t)blockIdx.x * kPend * kEpiThreads + et;
-    }
-
-    for (int i = 0; i < n_tiles; ++i) {
+    auto load_tile = [&](int i, float* v) {
       const int a = i % kAccStages;
       mbar_wait(bar_acc_full + 8 * a, (uint32_t)((i / kAccStages) & 1));
       tc_fence_after();
       if (threadIdx.x == 128) EVAVOS_TR(3, i);
-      float v[kCols];
       tmem_ld32(lane_addr + (uint32_t)(a * 128 + col0), v);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty + 8 * a);  // registers hold the tile: release the TMEM stage
       if (threadIdx.x == 128) EVAVOS_TR(4, i);
-      const int64_t n0 = (int64_t)(t0 + i) * kTilePos + col0;
-      if (n0 + kCols > p.n_pos) {
-        const int valid = (int)max((int64_t)0, p.n_pos - n0);
-        consume_tile<PASS, true>(v, cmax, thr, (int32_t)n0, valid, ps, pp, pending);
-      } else {
-        consume_tile<PASS, false>(v, cmax, thr, (int32_t)n0, kCols, ps, pp, pending);
-      }
-      if constexpr (PASS == 2) {
-        if (pending > kPend - kCols / 4) {  // the next tile stages at most kCols / 4 groups
-          flush_pending(ps, pp, pending, thr, p.cand, p.cand_cnt, q);
-          pending = 0;
-        }
-      }
-      if (threadIdx.x == 128) EVAVOS_TR(5, i);
-    }
+    };
 
-    if constexpr (PASS == 1) {
+    // ---- sweep 1: class maxima ----
+    {
+      float cmax[kCols];
+#pragma unroll
+      for (int j = 0; j < kCols; ++j) cmax[j] = kEmptyNh;
+      for (int i = 0; i < n_tiles; ++i) {
+        float v[kCols];
+        load_tile(i, v);
+        const int64_t n0 = (int64_t)tile_of(i) * kTilePos + col0;
+        int pending = 0;
+        if (n0 + kCols > p.n_pos) {
+          const int valid = (int)max((int64_t)0, p.n_pos - n0);
+          consume_tile<1, true>(v, cmax, 0.f, (int32_t)n0, valid, nullptr, nullptr, pending);
+        } else {
+          consume_tile<1, false>(v, cmax, 0.f, (int32_t)n0, kCols, nullptr, nullptr, pending);
+        }
+        if (threadIdx.x == 128) EVAVOS_TR(5, i);
+      }
       float4* dst = reinterpret_cast<float4*>(p.class_max + ((int64_t)chunk * p.nq_pad + q) * 128 + col0);
 #pragma unroll
       for (int j4 = 0; j4 < kCols / 4; ++j4)
         dst[j4] = make_float4(cmax[j4 * 4], cmax[j4 * 4 + 1], cmax[j4 * 4 + 2], cmax[j4 * 4 + 3]);
-    } else {
+    }
+
+    // ---- thresholds: every CTA of a query tile takes a slice of its 128 rows ----
+    epilogue_grid_barrier(p.grid_counter, gridDim.x);
+    {
+      const int r0 = (chunk * 128) / p.n_chunks, r1 = ((chunk + 1) * 128) / p.n_chunks;
+      for (int r = r0 + ew; r < r1; r += kEpiThreads / 32) {
+        const int64_t qq = (int64_t)m_tile * 128 + r;
+        if (qq < p.n_query) warp_threshold(p, qq, lane);
+      }
+    }
+    epilogue_grid_barrier(p.grid_counter, 2u * gridDim.x);
+
+    // ---- sweep 2: candidates ----
+    {
+      float thr = INFINITY;
+      if (q < p.n_query) thr = __ldcg(p.tau + q);
+      float4* ps = p.pend_score + (int64_t)blockIdx.x * kPend * kEpiThreads + et;
+      int32_t* pp = p.pend_pos + (int64_t)blockIdx.x * kPend * kEpiThreads + et;
+      int pending = 0;
+      float unused[1];
+      for (int i = n_tiles; i < n_iter; ++i) {
+        float v[kCols];
+        load_tile(i, v);
+        const int64_t n0 = (int64_t)tile_of(i) * kTilePos + col0;
+        if (n0 + kCols > p.n_pos) {
+          const int valid = (int)max((int64_t)0, p.n_pos - n0);
+          consume_tile<2, true>(v, unused, thr, (int32_t)n0, valid, ps, pp, pending);
+        } else {
+          consume_tile<2, false>(v, unused, thr, (int32_t)n0, kCols, ps, pp, pending);
+        }
+        if (pending > kPend - kCols / 4) {  // the next tile stages at most kCols / 4 groups
+          flush_pending(ps, pp, pending, thr, p.cand, p.cand_cnt, q);
+          pending = 0;
+        }
+        if (threadIdx.x == 128) EVAVOS_TR(5, i);
+      }
       if (pending > 0) flush_pending(ps, pp, pending, thr, p.cand, p.cand_cnt, q);
     }
   }
@@ -419,48 +499,56 @@ int score_pass_chunks(int64_t n_pos, int64_t n_query, int n_sm) {
   return (int)g;
 }
 
+size_t score_pass_pending_bytes(int64_t n_query, int n_chunks) {
+  return (size_t)ceil_div(n_query, 128) * n_chunks * kPend * kEpiThreads * (sizeof(float4) + sizeof(int32_t));
+}
+
 #ifdef EVAVOS_TRACE
 extern "C" int evavos_debug_trace(long long* out) {
   return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 6 * 64);
 }
 #endif
 
-size_t score_pass_pending_bytes(int64_t n_query, int n_chunks) {
-  return (size_t)ceil_div(n_query, 128) * n_chunks * kPend * kEpiThreads * (sizeof(float4) + sizeof(int32_t));
-}
-
-int launch_score_pass(int pass, const float* query, int64_t query_ch_stride, const void* key_tiles, int64_t n_pos,
-                      int64_t n_query, int n_chunks, float* class_max, const float* tau, int32_t* cand,
-                      int32_t* cand_cnt, void* pending, cudaStream_t st) {
-  PassParams p;
-  p.query = query;
-  p.query_ch_stride = query_ch_stride;
-  p.key_tiles = reinterpret_cast<const uint8_t*>(key_tiles);
-  p.n_pos = n_pos;
-  p.n_query = n_query;
-  p.n_mtiles = (int)ceil_div(n_query, 128);
-  p.nq_pad = (int64_t)p.n_mtiles * 128;
-  p.n_ktiles = (int)ceil_div(n_pos, kTilePos);
-  p.n_chunks = n_chunks;
-  p.class_max = class_max;
-  p.tau = tau;
-  p.cand = cand;
-  p.cand_cnt = cand_cnt;
-  const unsigned grid = (unsigned)(p.n_mtiles * n_chunks);
-  p.pend_score = reinterpret_cast<float4*>(pending);
-  p.pend_pos = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(pending) +
-                                          (size_t)grid * kPend * kEpiThreads * sizeof(float4));
+// Candidate generation for all queries: class maxima, thresholds and candidate lists in one cooperative launch
+// per wave of query tiles (one wave whenever n_query <= 128 * n_sm).
+int launch_score_select(const float* query, int64_t query_ch_stride, const void* key_tiles, const float* key_maxnorm,
+                        int64_t n_pos, int64_t n_query, int top_k, int n_chunks, int n_sm, float* class_max, float* tau,
+                        int32_t* cand, int32_t* cand_cnt, void* pending, unsigned int* grid_counter, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    EVAVOS_CUDA_OK(cudaFuncSetAttribute(score_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    EVAVOS_CUDA_OK(cudaFuncSetAttribute(score_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    EVAVOS_CUDA_OK(cudaFuncSetAttribute(score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  if (pass == 1)
-    score_pass_kernel<1><<<grid, kThreads, kSmemBytes, st>>>(p);
-  else
-    score_pass_kernel<2><<<grid, kThreads, kSmemBytes, st>>>(p);
-  EVAVOS_CUDA_OK(cudaGetLastError());
+  const int mt_total = (int)ceil_div(n_query, 128);
+  const int mt_per_launch = n_chunks > 1 ? mt_total : (mt_total < n_sm ? mt_total : n_sm);
+  for (int m0 = 0; m0 < mt_total; m0 += mt_per_launch) {
+    PassParams p;
+    p.query = query;
+    p.query_ch_stride = query_ch_stride;
+    p.key_tiles = reinterpret_cast<const uint8_t*>(key_tiles);
+    p.n_pos = n_pos;
+    p.n_query = n_query;
+    p.n_mtiles = mt_total - m0 < mt_per_launch ? mt_total - m0 : mt_per_launch;
+    p.nq_pad = (int64_t)mt_total * 128;
+    p.n_ktiles = (int)ceil_div(n_pos, kTilePos);
+    p.n_chunks = n_chunks;
+    p.class_max = class_max;
+    p.tau = tau;
+    p.cand = cand;
+    p.cand_cnt = cand_cnt;
+    p.key_maxnorm = key_maxnorm;
+    p.grid_counter = grid_counter;
+    p.m_tile0 = m0;
+    p.top_k = top_k;
+    const unsigned grid = (unsigned)(p.n_mtiles * n_chunks);
+    p.pend_score = reinterpret_cast<float4*>(pending);
+    p.pend_pos = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(pending) +
+                                            (size_t)mt_per_launch * n_chunks * kPend * kEpiThreads * sizeof(float4));
+    EVAVOS_CUDA_OK(cudaMemsetAsync(grid_counter, 0, sizeof(unsigned int), st));
+    void* args[] = {&p};
+    EVAVOS_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(score_select_kernel), dim3(grid),
+                                               dim3(kThreads), args, kSmemBytes, st));
+  }
   return EVAVOS_OK;
 }
 

@@ -6,8 +6,6 @@
 //                       selection in EVAVOS_PATH_SIMT and the overflow path of the tcgen05
 //                       filter (queries whose candidate list exceeded kCandCap, e.g. banks
 //                       with thousands of tied keys).
-//  threshold_kernel     k-th largest of the 128 per-class maxima produced by pass 1 of the
-//                       tcgen05 filter -> per-query admission threshold for pass 2.
 //  finalize_kernel      exact rescoring of <= kCandCap candidates, top-k by (score desc,
 //                       position asc), softmax over the survivors
 //                       (softmax_w_g_top, prop_net.py:53-57).
@@ -212,45 +210,6 @@ __global__ void __launch_bounds__(256) brute_select_kernel(
   }
 }
 
-// One 128-thread CTA per query, one thread per column class: maximum over the memory-axis chunks, then the
-// k-th largest of the 128 class maxima by all-pairs ranking in shared memory.
-__global__ void __launch_bounds__(128) threshold_kernel(
-    const float* __restrict__ class_max, int n_chunks, int64_t n_query, int64_t nq_pad, int top_k,
-    const float* __restrict__ query, int64_t query_ch_stride, const float* __restrict__ key_maxnorm,
-    float* __restrict__ tau, int32_t* __restrict__ cand_cnt) {
-  __shared__ unsigned long long keys[128];
-  __shared__ float warp_sq[4];
-  const int tid = threadIdx.x;
-  const int64_t q = blockIdx.x;
-  float v = kEmptyNh;
-#pragma unroll 8
-  for (int g = 0; g < n_chunks; ++g) v = fmaxf(v, __ldg(class_max + ((int64_t)g * nq_pad + q) * 128 + tid));
-  // |q|^2 over the 64 key channels
-  float qsq = 0.f;
-  if (tid < 64) {
-    const float a = __ldg(query + (int64_t)tid * query_ch_stride + q);
-    qsq = a * a;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) qsq += __shfl_xor_sync(0xffffffffu, qsq, o);
-  if ((tid & 31) == 0) warp_sq[tid >> 5] = qsq;
-  const unsigned long long mine = ((unsigned long long)float_to_ordered(v) << 32) | (unsigned long long)(127 - tid);
-  keys[tid] = mine;
-  __syncthreads();
-  int rank = 0;
-#pragma unroll 8
-  for (int j = 0; j < 128; ++j) rank += keys[j] > mine ? 1 : 0;
-  if (rank == top_k - 1) {  // exactly one thread: keys are unique
-    const float qn = sqrtf(warp_sq[0] + warp_sq[1]) * 1.0001f;
-    const float kn = *key_maxnorm;
-    // |q^.k^ - q.k| <= 2^-8 (1 + 2^-10) |q||k| for bf16 round-to-nearest operands, plus slack for the
-    // tensor-core fp32 accumulation and the rounding of -|k|^2/2.
-    const float eps = 0.004f * qn * kn + 2.0e-6f * kn * kn + 1.0e-30f;
-    tau[q] = v - 2.0f * eps;
-    cand_cnt[q] = 0;
-  }
-}
-
 // One 128-thread CTA per query.  Every thread rescoring one (or two) candidates exactly, keys go to shared
 // memory, each thread ranks its candidates all-pairs (rank = number of candidates with a larger
 // (score, -position) key), and the first top_k ranks are written best-first with their softmax weights.
@@ -331,15 +290,6 @@ int launch_brute_select(const float* key_pm, const float* query, int64_t query_c
   if (grid > 0x7fffffff) grid = 0x7fffffff;
   brute_select_kernel<<<(unsigned)grid, 256, 0, st>>>(key_pm, query, query_ch_stride, CK, n_pos, n_query, top_k,
                                                       only_overflow, cand, cand_cnt);
-  EVAVOS_CUDA_OK(cudaGetLastError());
-  return EVAVOS_OK;
-}
-
-int launch_threshold(const float* class_max, int n_chunks, int64_t n_query, int64_t nq_pad, int top_k,
-                     const float* query, int64_t query_ch_stride, const float* key_maxnorm, float* tau,
-                     int32_t* cand_cnt, cudaStream_t st) {
-  threshold_kernel<<<(unsigned)n_query, 128, 0, st>>>(class_max, n_chunks, n_query, nq_pad, top_k, query,
-                                                                  query_ch_stride, key_maxnorm, tau, cand_cnt);
   EVAVOS_CUDA_OK(cudaGetLastError());
   return EVAVOS_OK;
 }
