@@ -17,10 +17,10 @@
 // Both sweeps run inside ONE cooperative launch (score_select_kernel): the TMA and MMA warps simply stream the
 // chunk's tiles twice and run ahead into sweep 2 while the epilogue warps exchange thresholds.
 //
-// Roles per CTA (640 threads, 1 CTA/SM, one wave): warps 0 and 3 = TMA producers (cp.async.bulk of
-// pre-swizzled 20 KB key tile images; one issuing thread sustains only ~50 B/clk, two reach the L2
-// rate), warp 1 = MMA issuer (one elected lane, 5 x tcgen05.mma 128x128x16 per tile), warp 2 = TMEM
-// allocator, warps 4-19 = epilogue (four warpgroups, each thread owns one query row and 32
+// Roles per CTA (640 threads, 1 CTA/SM, one wave): warp 0 = TMA producers (4 lanes issuing cp.async.bulk of
+// pre-swizzled 20 KB key tile images; one issuing thread keeps a single copy in flight, ~50 B/clk),
+// warps 1-2 = MMA issuers (one elected lane each, alternating tiles, 5 x tcgen05.mma 128x128x16 per tile),
+// warp 3 = TMEM allocator, warps 4-19 = epilogue (four warpgroups, each thread owns one query row and 32
 // accumulator columns; branch-free inner loops).  Rings: 6 shared-memory key stages, 4 TMEM
 // accumulator stages (4 x 128 columns = all 512).  The query tile is converted to bf16 and
 // swizzled into shared memory by the CTA itself.
@@ -44,6 +44,7 @@ constexpr int kAccStages = 3;   // 3 x 128 accumulator columns; the query operan
 constexpr int kQueryCol = 384;
 constexpr int kThreads = 640;
 constexpr int kEpiThreads = 512;
+constexpr int kProducers = 4;   // TMA-issuing lanes of warp 0 (kStages % kProducers == 0)
 constexpr int kCols = 32;       // accumulator columns per epilogue thread
 constexpr int kPend = 16;       // staged hit groups per epilogue thread (flushed when more than half full)
 constexpr int kBarBytes = 256;
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 3) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
   // The first ring of key tiles does not depend on anything below: get it in flight now.
   if (threadIdx.x == 0) {
     const int pre = n_iter < kStages ? n_iter : kStages;
-    for (int i = 0; i < pre; i += 2) {  // even iterations belong to this producer (warp 0), odd ones to warp 3
+    for (int i = 0; i < pre; ++i) {
       mbar_arrive_expect_tx(bar_full + 8 * i, kTileBytes);
       bulk_g2s(stage0 + i * kTileBytes, p.key_tiles + (int64_t)tile_of(i) * kTileBytes, kTileBytes, bar_full + 8 * i);
     }
@@ -357,11 +358,12 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
   __syncthreads();
   tc_fence_after();
 
-  if (warp == 0 || warp == 3) {
-    // ===== TMA producers: warp 0 streams the even iterations, warp 3 the odd ones =====
-    if (lane == 0) {
-      // warp 0 already issued its iterations below kStages in the prologue
-      for (int i = (warp == 0 ? kStages : 1); i < n_iter; i += 2) {
+  if (warp == 0) {
+    // ===== TMA producers: kProducers lanes, lane l streams iterations i = l (mod kProducers) =====
+    // (one thread keeps only one bulk copy in flight; several lanes keep several)
+    if (lane < kProducers) {
+      // iterations below kStages were issued in the prologue
+      for (int i = kStages + lane; i < n_iter; i += kProducers) {
         const int s = i % kStages;
         const uint32_t ph = (uint32_t)((i / kStages) & 1);
         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
@@ -370,10 +372,13 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
         bulk_g2s(stage0 + s * kTileBytes, p.key_tiles + (int64_t)tile_of(i) * kTileBytes, kTileBytes, bar_full + 8 * s);
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (warp == 1 || warp == 2) {
+    // ===== MMA issuers: warp 1 takes the even iterations, warp 2 the odd ones =====
+    // (measured: one thread spends ~350 clk per tile in its two barrier waits; two threads overlap them with the
+    //  other's MMAs: 830 -> 600 clk per tile.  Three threads, or one thread interleaving two tiles, were slower.
+    //  Each commit tracks the MMAs of its own thread, which is exactly one tile.)
     const uint32_t a_tmem = tmem_base + kQueryCol;
-    for (int i = 0; i < n_iter; ++i) {
+    for (int i = warp - 1; i < n_iter; i += 2) {
       const int s = i % kStages, a = i % kAccStages;
       mbar_wait(bar_full + 8 * s, (uint32_t)((i / kStages) & 1));
       mbar_wait(bar_acc_empty + 8 * a, (uint32_t)(((i / kAccStages) & 1) ^ 1));
@@ -483,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 2) {
+  if (warp == 3) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }

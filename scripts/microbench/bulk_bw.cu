@@ -31,8 +31,13 @@ __global__ void __launch_bounds__(128, 1) k(const uint8_t* buf, int n_buf_tiles,
   }
   __syncthreads();
   long long t0 = clock64();
+#ifdef KLANES
+  if (threadIdx.x < KPROD) {
+    const int pw = threadIdx.x;
+#else
   if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < KPROD) {
     const int pw = threadIdx.x >> 5;
+#endif
     const int grp = blockIdx.x / 13, mem = blockIdx.x % 13;
     auto tile_index = [&](int i) -> int {
       if (mode == 0) return (blockIdx.x * tiles_per_cta + i) % n_buf_tiles;
