@@ -71,7 +71,7 @@ Carve carve_workspace(const EvavosMemReadArgs& a, int n_chunks, uint8_t* base) {
   c.sb.cand_cnt = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * nq_pad));
   c.sb.cand = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * nq_pad * kCandCap));
   c.sb.pending = take(n_chunks > 0 ? score_pass_pending_bytes(a.n_query, n_chunks) : 0);
-  c.sb.grid_counter = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int)));
+  c.sb.grid_counter = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * (size_t)mt));
   c.idx = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * a.n_query * a.top_k));
   c.weight = reinterpret_cast<float*>(take(sizeof(float) * a.n_query * a.top_k));
   c.total = off + 1024;  // slack for aligning the caller's pointer

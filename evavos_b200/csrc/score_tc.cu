@@ -162,7 +162,7 @@ struct PassParams {
   float4* pend_score;   // [grid][kPend][kEpiThreads] scores of staged hit groups (pass 2)
   int32_t* pend_pos;    // [grid][kPend][kEpiThreads] first position of each staged group
   const float* key_maxnorm;
-  unsigned int* grid_counter;  // zeroed before every launch
+  unsigned int* grid_counter;  // one counter per query tile of the launch, zeroed before every launch
   int m_tile0;          // first query tile of this launch
   int top_k;
 };
@@ -220,55 +220,87 @@ __device__ __forceinline__ void consume_tile(const float* v, float* cmax, float 
   }
 }
 
-// Grid-wide barrier among the epilogue threads of all CTAs (the grid is launched cooperatively, so every
-// CTA is resident).  `counter` only grows: the n-th barrier waits for n * gridDim.x arrivals.
+// Barrier among the epilogue threads of the CTAs that share a query tile (the grid is launched cooperatively,
+// so every CTA is resident).  `counter` only grows: the n-th barrier waits for n * n_chunks arrivals.
 __device__ __forceinline__ void epilogue_grid_barrier(unsigned int* counter, unsigned int target) {
   asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
   if (threadIdx.x == 128) {
-    __threadfence();
-    atomicAdd(counter, 1u);
+    // release: cumulative over the CTA's writes ordered before the bar.sync above
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     unsigned int seen;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-      if (seen < target) __nanosleep(64);
     } while (seen < target);
-    __threadfence();
   }
   asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 }
 
 // Admission threshold of one query (one warp): k-th largest of its 128 class maxima (4 per lane, maximum over the
-// memory-axis chunks) by a 32-step radix descent on order-preserving keys, minus the bf16 error margin.
+// memory-axis chunks) by an in-warp bitonic sort, minus the bf16 error margin.
 __device__ __forceinline__ void warp_threshold(const PassParams& p, int64_t q, int lane) {
-  float v[4] = {kEmptyNh, kEmptyNh, kEmptyNh, kEmptyNh};
-  for (int g = 0; g < p.n_chunks; ++g) {
-    const float* row = p.class_max + ((int64_t)g * p.nq_pad + q) * 128;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) v[t] = fmaxf(v[t], __ldcg(row + lane + 32 * t));  // written by other CTAs: bypass L1
-  }
   const float qa = __ldg(p.query + (int64_t)lane * p.query_ch_stride + q);
   const float qb = __ldg(p.query + (int64_t)(lane + 32) * p.query_ch_stride + q);
+  float v[4] = {kEmptyNh, kEmptyNh, kEmptyNh, kEmptyNh};
+  {
+    // 8 chunks x 4 classes = 32 independent L2 loads per round (the rows were written by other CTAs: bypass L1)
+    const float* row0 = p.class_max + q * 128 + lane;
+    const int64_t chunk_stride = p.nq_pad * 128;
+    for (int g = 0; g < p.n_chunks; g += 8) {
+      float w[8][4];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          w[u][t] = (g + u < p.n_chunks) ? __ldcg(row0 + (g + u) * chunk_stride + 32 * t) : kEmptyNh;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) v[t] = fmaxf(v[t], w[u][t]);
+    }
+  }
   float qsq = fmaf(qa, qa, qb * qb);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) qsq += __shfl_xor_sync(0xffffffffu, qsq, o);
-  uint32_t key[4];
+  // k-th largest of the warp's 128 values: bitonic sort, descending, element e = 4 * lane + t.
+  // Partners e ^ j with j < 4 sit in the same lane (register swap), j >= 4 in lane ^ (j / 4) (shuffle).
 #pragma unroll
-  for (int t = 0; t < 4; ++t) key[t] = float_to_ordered(v[t]);
-  uint32_t pfx = 0;
-  for (int bit = 31; bit >= 0; --bit) {
-    const uint32_t trial = pfx | (1u << bit);
-    int cnt = 0;
+  for (int k = 2; k <= 128; k <<= 1) {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) cnt += __popc(__ballot_sync(0xffffffffu, key[t] >= trial));
-    if (cnt >= p.top_k) pfx = trial;
+    for (int j = k >> 1; j >= 1; j >>= 1) {
+      if (j >= 4) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int e = 4 * lane + t;
+          const float other = __shfl_xor_sync(0xffffffffu, v[t], j >> 2);
+          const bool keep_max = ((e & k) == 0) == ((e & j) == 0);   // descending blocks keep the larger in front
+          v[t] = keep_max ? fmaxf(v[t], other) : fminf(v[t], other);
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if ((t & j) == 0) {
+            const int e = 4 * lane + t;
+            const float a = v[t], b = v[t | j];
+            const bool desc = (e & k) == 0;
+            v[t] = desc ? fmaxf(a, b) : fminf(a, b);
+            v[t | j] = desc ? fminf(a, b) : fmaxf(a, b);
+          }
+        }
+      }
+    }
   }
+  const int kth = p.top_k - 1;
+  float sel = v[0];
+#pragma unroll
+  for (int t = 1; t < 4; ++t) sel = ((kth & 3) == t) ? v[t] : sel;
+  const float kth_value = __shfl_sync(0xffffffffu, sel, kth >> 2);
   if (lane == 0) {
     const float qn = sqrtf(qsq) * 1.0001f;
     const float kn = *p.key_maxnorm;
     // |q^.k^ - q.k| <= 2^-8 (1 + 2^-10) |q||k| for bf16 round-to-nearest operands, plus slack for the
     // tensor-core fp32 accumulation and the rounding of -|k|^2/2.
     const float eps = 0.004f * qn * kn + 2.0e-6f * kn * kn + 1.0e-30f;
-    p.tau[q] = ordered_to_float(pfx) - 2.0f * eps;
+    p.tau[q] = kth_value - 2.0f * eps;
     p.cand_cnt[q] = 0;
   }
 }
@@ -447,7 +479,9 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
     }
 
     // ---- thresholds: every CTA of a query tile takes a slice of its 128 rows ----
-    epilogue_grid_barrier(p.grid_counter, gridDim.x);
+    if (threadIdx.x == 128) EVAVOS_TR(0, 60);
+    epilogue_grid_barrier(p.grid_counter + (blockIdx.x % p.n_mtiles), (unsigned)p.n_chunks);
+    if (threadIdx.x == 128) EVAVOS_TR(0, 61);
     {
       const int r0 = (chunk * 128) / p.n_chunks, r1 = ((chunk + 1) * 128) / p.n_chunks;
       for (int r = r0 + ew; r < r1; r += kEpiThreads / 32) {
@@ -455,7 +489,9 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
         if (qq < p.n_query) warp_threshold(p, qq, lane);
       }
     }
-    epilogue_grid_barrier(p.grid_counter, 2u * gridDim.x);
+    if (threadIdx.x == 128) EVAVOS_TR(0, 62);
+    epilogue_grid_barrier(p.grid_counter + (blockIdx.x % p.n_mtiles), 2u * (unsigned)p.n_chunks);
+    if (threadIdx.x == 128) EVAVOS_TR(0, 63);
 
     // ---- sweep 2: candidates ----
     {
@@ -549,7 +585,7 @@ int launch_score_select(const float* query, int64_t query_ch_stride, const void*
     p.pend_score = reinterpret_cast<float4*>(pending);
     p.pend_pos = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(pending) +
                                             (size_t)mt_per_launch * n_chunks * kPend * kEpiThreads * sizeof(float4));
-    EVAVOS_CUDA_OK(cudaMemsetAsync(grid_counter, 0, sizeof(unsigned int), st));
+    EVAVOS_CUDA_OK(cudaMemsetAsync(grid_counter, 0, sizeof(unsigned int) * (size_t)p.n_mtiles, st));
     void* args[] = {&p};
     EVAVOS_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(score_select_kernel), dim3(grid),
                                                dim3(kThreads), args, kSmemBytes, st));
