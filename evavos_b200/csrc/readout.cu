@@ -20,23 +20,26 @@ __device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
   a.w = fmaf(w, v.w, a.w);
 }
 
-// fp32 rows, CV = 128 * NV.  grid (ceil(nq/8), K), 256 threads.
+// fp32 rows; each CTA covers 128 * NV channels starting at blockIdx.z * 128 * NV of rows that are CV floats long.
+// grid (ceil(nq/8), K, CV / (128 * NV)), 256 threads.
 template <int NV>
 __global__ void __launch_bounds__(256) readout_f32_kernel(
-    const float* __restrict__ val_pm, int64_t capacity_pos, const int32_t* __restrict__ idx,
-    const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out,
+    const float* __restrict__ val_pm_all, int64_t capacity_pos, int CVfull, const int32_t* __restrict__ idx,
+    const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out_all,
     int64_t out_obj_stride, int64_t out_ch_stride) {
   constexpr int CV = 128 * NV;
   __shared__ float st[CV][kQPerCta + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int o = blockIdx.y;
+  const float* val_pm = val_pm_all + (int64_t)blockIdx.z * CV;
+  float* out = out_all + (int64_t)blockIdx.z * CV * out_ch_stride;
   const int64_t q0 = (int64_t)blockIdx.x * kQPerCta;
   const int64_t q = q0 + warp;
   float4 acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (q < n_query) {
-    const float* vbase = val_pm + (int64_t)o * capacity_pos * CV;
+    const float* vbase = val_pm + (int64_t)o * capacity_pos * CVfull;
     for (int jb = 0; jb < top_k; jb += 32) {
       const int jj = jb + lane;
       const int32_t my_n = jj < top_k ? idx[q * top_k + jj] : -1;
@@ -47,7 +50,7 @@ __global__ void __launch_bounds__(256) readout_f32_kernel(
         const int32_t n = __shfl_sync(0xffffffffu, my_n, j);
         const float w = __shfl_sync(0xffffffffu, my_w, j);
         if (n < 0) continue;
-        const float4* row = reinterpret_cast<const float4*>(vbase + (int64_t)n * CV) + lane;
+        const float4* row = reinterpret_cast<const float4*>(vbase + (int64_t)n * CVfull) + lane;
 #pragma unroll
         for (int i = 0; i < NV; ++i) fma4(acc[i], w, __ldg(row + 32 * i));
       }
@@ -172,19 +175,23 @@ int launch_readout(const EvavosBankShadow& b, const int32_t* idx, const float* w
   if (out_obj_stride == 0) out_obj_stride = (int64_t)b.CV * n_query;
   const dim3 grid((unsigned)ceil_div(n_query, kQPerCta), (unsigned)b.K);
   const bool row16 = (reinterpret_cast<uintptr_t>(b.val_pm) % 16) == 0;
-#define EVAVOS_RO_F32(NV)                                                                                  \
-  readout_f32_kernel<NV><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(b.val_pm), b.capacity_pos, idx, \
-                                               weight, n_query, top_k, out, out_obj_stride, out_ch_stride)
+#define EVAVOS_RO_F32(NV, SPLIT)                                                                           \
+  readout_f32_kernel<NV><<<dim3(grid.x, grid.y, SPLIT), 256, 0, st>>>(                                     \
+      reinterpret_cast<const float*>(b.val_pm), b.capacity_pos, b.CV, idx, weight, n_query, top_k, out,    \
+      out_obj_stride, out_ch_stride)
 #define EVAVOS_RO_BF16(NV)                                                                                  \
   readout_bf16_kernel<NV><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(b.val_pm),           \
                                                 b.capacity_pos, idx, weight, n_query, top_k, out,           \
                                                 out_obj_stride, out_ch_stride)
   if (b.val_dtype == EVAVOS_F32 && row16 && b.CV % 128 == 0 && b.CV <= 512) {
+    // Splitting a row's channels over two CTAs (more resident warps) was measured SLOWER on B200 (55 vs 42 us at
+    // cfg2: twice the L2 requests at half the size), so one warp keeps a whole value row.
+    const bool split = false;
     switch (b.CV / 128) {
-      case 1: EVAVOS_RO_F32(1); break;
-      case 2: EVAVOS_RO_F32(2); break;
-      case 3: EVAVOS_RO_F32(3); break;
-      default: EVAVOS_RO_F32(4); break;
+      case 1: EVAVOS_RO_F32(1, 1); break;
+      case 2: if (split) EVAVOS_RO_F32(1, 2); else EVAVOS_RO_F32(2, 1); break;
+      case 3: EVAVOS_RO_F32(3, 1); break;
+      default: if (split) EVAVOS_RO_F32(2, 2); else EVAVOS_RO_F32(4, 1); break;
     }
   } else if (b.val_dtype == EVAVOS_BF16 && row16 && b.CV % 256 == 0 && b.CV <= 512) {
     if (b.CV == 256) EVAVOS_RO_BF16(1);

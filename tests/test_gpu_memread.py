@@ -166,3 +166,31 @@ def test_multi_frame_query_batch():
     for f in range(3):
         single, _ = ev.memory_read(bank, qk3[:, :, f].to(dev), 50)
         assert torch.equal(batched[:, :, f], single)
+
+
+@pytest.mark.parametrize("cv", [512, 256, 96])
+def test_bf16_value_bank(cv):
+    """bf16 mode (BASELINE.json configs[4]): both sides get bf16-representable inputs, the reference evaluates them
+    in fp32; the bf16 value shadow + fp32 accumulation must stay within 1e-2 relative (in fact ~1e-6: the rounding
+    is lossless on representable inputs)."""
+    import evavos_b200 as ev
+    dev = torch.device("cuda:0")
+    mk, qk, mv = synth(41, 64, cv, 4, 9, 12, 2)
+    mk, qk, mv = (t.to(torch.bfloat16).float() for t in (mk, qk, mv))
+    bank = ev.MemoryBank.from_tensors(mk.to(dev), mv.to(dev), value_dtype=torch.bfloat16)
+    assert bank.val_pm.dtype == torch.bfloat16
+    out, aff = ev.memory_read(bank, qk.to(dev), 50, want_topk=True)
+    tk, ro = onp.memory_read(mk[0].reshape(64, -1).numpy(), qk[0].reshape(64, -1).numpy(), mv.reshape(2, cv, -1).numpy(), 50)
+    exact, tie, bad, _ = onp.compare_topk(aff.idx.cpu().numpy(), onp.affinity_scores(mk[0].reshape(64, -1).numpy(),
+                                                                                     qk[0].reshape(64, -1).numpy()), 50, TIE_TOL)
+    assert bad == 0
+    err = onp.rel_l2(out.cpu().numpy().reshape(ro.shape), ro)
+    assert err < 1e-2, err
+    if tie == 0:
+        assert err < 1e-5, err
+    # arbitrary fp32 values stored in a bf16 shadow: rounding error of the values only, well inside 1e-2
+    mk2, qk2, mv2 = synth(42, 64, cv, 4, 9, 12, 2)
+    bank2 = ev.MemoryBank.from_tensors(mk2.to(dev), mv2.to(dev), value_dtype=torch.bfloat16)
+    out2, _ = ev.memory_read(bank2, qk2.to(dev), 50)
+    _, ro2 = onp.memory_read(mk2[0].reshape(64, -1).numpy(), qk2[0].reshape(64, -1).numpy(), mv2.reshape(2, cv, -1).numpy(), 50)
+    assert onp.rel_l2(out2.cpu().numpy().reshape(ro2.shape), ro2) < 1e-2
