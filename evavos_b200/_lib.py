@@ -67,6 +67,8 @@ SIGNATURES = {
     "evavos_memread_host": (_c_i32, [_c_vp, _c_vp, _c_vp, _c_i32, _c_i32, _c_i32, _c_i64, _c_i64, _c_i32, _c_i32,
                                      _c_vp, _c_vp, _c_vp, ctypes.POINTER(_c_i64), ctypes.POINTER(_c_i64)]),
     "evavos_release_host_scratch": (_c_i32, []),
+    "evavos_stage_timing": (_c_i32, [_c_i32]),
+    "evavos_stage_timing_read": (_c_i32, [ctypes.POINTER(ctypes.c_float)]),
 }
 
 

@@ -173,6 +173,32 @@ size_t evavos_memread_workspace_bytes(const EvavosMemReadArgs* args) {
   return carve_workspace(*args, chunks, nullptr).total;
 }
 
+// ---- optional per-stage timing of evavos_memread (diagnostics; CUDA events on the caller's stream) ----------
+namespace {
+bool g_timing = false;
+cudaEvent_t g_ev[5];
+bool g_ev_made = false;
+inline void stage_mark(int i, cudaStream_t st) {
+  if (g_timing) cudaEventRecord(g_ev[i], st);
+}
+}  // namespace
+
+int evavos_stage_timing(int32_t enable) {
+  if (enable && !g_ev_made) {
+    for (int i = 0; i < 5; ++i) EVAVOS_CUDA_OK(cudaEventCreate(&g_ev[i]));
+    g_ev_made = true;
+  }
+  g_timing = enable != 0;
+  return EVAVOS_OK;
+}
+
+int evavos_stage_timing_read(float* ms4) {
+  if (!g_ev_made || !ms4) { set_error("stage timing not enabled"); return EVAVOS_ERR_INVALID; }
+  EVAVOS_CUDA_OK(cudaEventSynchronize(g_ev[4]));
+  for (int i = 0; i < 4; ++i) EVAVOS_CUDA_OK(cudaEventElapsedTime(&ms4[i], g_ev[i], g_ev[i + 1]));
+  return EVAVOS_OK;
+}
+
 int evavos_memread(const EvavosMemReadArgs* a, evavos_stream_t stream) {
   int rc = validate_read(a);
   if (rc) return rc;
@@ -192,28 +218,34 @@ int evavos_memread(const EvavosMemReadArgs* a, evavos_stream_t stream) {
   const Carve c = carve_workspace(*a, chunks, base);
   const int CK = a->bank.CK;
 
+  int32_t* idx = a->topk_idx ? a->topk_idx : c.idx;
+  float* weight = a->topk_weight ? a->topk_weight : c.weight;
+
   // 1. candidate generation (the query is consumed in the caller's layout; no query shadow)
+  stage_mark(0, st);
   if (tensor) {
     rc = launch_score_select(a->query, a->query_ch_stride, a->bank.key_tiles, a->bank.key_maxnorm, a->n_pos, a->n_query,
                              a->top_k, chunks, n_sm, c.sb.class_max, c.sb.tau, c.sb.cand, c.sb.cand_cnt, c.sb.pending,
                              c.sb.grid_counter, st);
     if (rc) return rc;
-    // queries whose candidate list overflowed (massive ties) are redone exactly
+    stage_mark(1, st);
+    // queries whose candidate list overflowed (massive ties) are redone exactly; a no-op launch otherwise
     rc = launch_brute_select(a->bank.key_pm, a->query, a->query_ch_stride, CK, a->n_pos, a->n_query, a->top_k, 1,
                              c.sb.cand, c.sb.cand_cnt, n_sm, st);
     if (rc) return rc;
   } else {
+    stage_mark(1, st);
     rc = launch_brute_select(a->bank.key_pm, a->query, a->query_ch_stride, CK, a->n_pos, a->n_query, a->top_k, 0,
                              c.sb.cand, c.sb.cand_cnt, n_sm, st);
     if (rc) return rc;
   }
+  stage_mark(2, st);
 
   // 2. exact rescoring, top-k, softmax
-  int32_t* idx = a->topk_idx ? a->topk_idx : c.idx;
-  float* weight = a->topk_weight ? a->topk_weight : c.weight;
   rc = launch_finalize(a->bank.key_pm, a->query, a->query_ch_stride, CK, a->n_query, a->top_k, c.sb.cand,
-                       c.sb.cand_cnt, idx, weight, a->topk_score, st);
+                       c.sb.cand_cnt, nullptr, idx, weight, a->topk_score, st);
   if (rc) return rc;
+  stage_mark(3, st);
 
   // 3. sparse readout for all objects
   if (a->readout) {
@@ -221,6 +253,7 @@ int evavos_memread(const EvavosMemReadArgs* a, evavos_stream_t stream) {
                         a->readout_ch_stride, st);
     if (rc) return rc;
   }
+  stage_mark(4, st);
   return EVAVOS_OK;
 }
 

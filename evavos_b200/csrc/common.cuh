@@ -87,8 +87,8 @@ int launch_brute_select(const float* key_pm, const float* query, int64_t query_c
                         int64_t n_query, int top_k, int only_overflow, int32_t* cand, int32_t* cand_cnt, int n_sm,
                         cudaStream_t st);
 int launch_finalize(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_query,
-                    int top_k, const int32_t* cand, const int32_t* cand_cnt, int32_t* out_idx, float* out_weight,
-                    float* out_score, cudaStream_t st);
+                    int top_k, const int32_t* cand, const int32_t* cand_cnt, const int32_t* only_flag, int32_t* out_idx,
+                    float* out_weight, float* out_score, cudaStream_t st);
 int launch_score_select(const float* query, int64_t query_ch_stride, const void* key_tiles, const float* key_maxnorm,
                         int64_t n_pos, int64_t n_query, int top_k, int n_chunks, int n_sm, float* class_max, float* tau,
                         int32_t* cand, int32_t* cand_cnt, void* pending, unsigned int* grid_counter, cudaStream_t st);

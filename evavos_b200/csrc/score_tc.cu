@@ -16,6 +16,8 @@
 //            contains the exact fp32 top-k.  finalize_kernel's exact rescoring picks it.
 // Both sweeps run inside ONE cooperative launch (score_select_kernel): the TMA and MMA warps simply stream the
 // chunk's tiles twice and run ahead into sweep 2 while the epilogue warps exchange thresholds.
+// (Running the exact finalizer inside this kernel as well was measured slower: a CTA finalizes its dozen queries
+// in sequence, while the separate finalize_kernel runs all queries at once.)
 //
 // Roles per CTA (640 threads, 1 CTA/SM, one wave): warp 0 = TMA producers (4 lanes issuing cp.async.bulk of
 // pre-swizzled 20 KB key tile images; one issuing thread keeps a single copy in flight, ~50 B/clk),
@@ -323,6 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(base_ptr + kTileBytes * kStages + 16 * kStages + 16 * kAccStages);
 
+  if (threadIdx.x == 0) EVAVOS_TR(0, 56);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = p.m_tile0 + blockIdx.x % p.n_mtiles;
   const int chunk = blockIdx.x / p.n_mtiles;
@@ -389,6 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (threadIdx.x == 0) EVAVOS_TR(0, 57);
 
   if (warp == 0) {
     // ===== TMA producers: kProducers lanes, lane l streams iterations i = l (mod kProducers) =====
@@ -518,6 +522,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
         if (threadIdx.x == 128) EVAVOS_TR(5, i);
       }
       if (pending > 0) flush_pending(ps, pp, pending, thr, p.cand, p.cand_cnt, q);
+      if (threadIdx.x == 128) EVAVOS_TR(0, 58);
     }
   }
 
@@ -527,6 +532,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
   if (warp == 3) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
+  if (threadIdx.x == 96) EVAVOS_TR(0, 59);
 }
 
 }  // namespace

@@ -12,45 +12,11 @@
 //
 // All three agree on one arithmetic for a score: see dot_row / affinity_from_parts.
 #include "common.cuh"
+#include "select_common.cuh"
 
 namespace evavos {
 
 namespace {
-
-// kk += |k|^2, kq += k.q over CK channels, channel order 0..CK-1, one FMA per term.
-__device__ __forceinline__ void dot_row(const float4* __restrict__ krow, const float* __restrict__ q, int CK,
-                                        float& kk, float& kq) {
-  kk = 0.f;
-  kq = 0.f;
-  if (CK == 64) {  // the network's key width: all 16 row loads in flight before the first FMA
-    float4 kv[16];
-#pragma unroll
-    for (int c4 = 0; c4 < 16; ++c4) kv[c4] = __ldg(krow + c4);
-#pragma unroll
-    for (int c4 = 0; c4 < 16; ++c4) {
-      const float4 qv = *reinterpret_cast<const float4*>(q + 4 * c4);
-      kk = fmaf(kv[c4].x, kv[c4].x, kk); kq = fmaf(kv[c4].x, qv.x, kq);
-      kk = fmaf(kv[c4].y, kv[c4].y, kk); kq = fmaf(kv[c4].y, qv.y, kq);
-      kk = fmaf(kv[c4].z, kv[c4].z, kk); kq = fmaf(kv[c4].z, qv.z, kq);
-      kk = fmaf(kv[c4].w, kv[c4].w, kk); kq = fmaf(kv[c4].w, qv.w, kq);
-    }
-    return;
-  }
-  for (int c4 = 0; c4 < (CK >> 2); ++c4) {
-    const float4 kv = __ldg(krow + c4);
-    const float4 qv = *reinterpret_cast<const float4*>(q + 4 * c4);
-    kk = fmaf(kv.x, kv.x, kk); kq = fmaf(kv.x, qv.x, kq);
-    kk = fmaf(kv.y, kv.y, kk); kq = fmaf(kv.y, qv.y, kq);
-    kk = fmaf(kv.z, kv.z, kk); kq = fmaf(kv.z, qv.z, kq);
-    kk = fmaf(kv.w, kv.w, kk); kq = fmaf(kv.w, qv.w, kq);
-  }
-}
-
-__device__ __forceinline__ float sumsq(const float* __restrict__ q, int CK) {
-  float s = 0.f;
-  for (int c = 0; c < CK; ++c) s = fmaf(q[c], q[c], s);
-  return s;
-}
 
 constexpr int kBruteQ = 4;  // queries per CTA pass
 
@@ -210,73 +176,19 @@ __global__ void __launch_bounds__(256) brute_select_kernel(
   }
 }
 
-// One 128-thread CTA per query.  Every thread rescoring one (or two) candidates exactly, keys go to shared
-// memory, each thread ranks its candidates all-pairs (rank = number of candidates with a larger
-// (score, -position) key), and the first top_k ranks are written best-first with their softmax weights.
-// The work per query is tiny; the kernel is latency-bound, so it runs all queries at once (about 11
-// resident CTAs per SM at 480p) and keeps every candidate's row loads independent.
+// One 128-thread CTA per query (see finalize_query).  Measured on B200: ~20 us for 1620 queries whether a CTA takes
+// one query or four, and whether a candidate row is read by one thread or four - neither launch rate nor the
+// row loads bound it; a round-2 item.  only_flag != nullptr: only queries flagged there.
 __global__ void __launch_bounds__(128) finalize_kernel(
     const float* __restrict__ key_pm, const float* __restrict__ query, int64_t query_ch_stride, int CK,
     int64_t n_query, int top_k, const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
-    int32_t* __restrict__ out_idx, float* __restrict__ out_weight, float* __restrict__ out_score) {
-  __shared__ __align__(16) float qs[64];
-  __shared__ unsigned long long keys[kCandCap];
-  __shared__ unsigned long long sel[EVAVOS_MAX_TOPK];
-  __shared__ float warp_sum[4];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t* __restrict__ only_flag, int32_t* __restrict__ out_idx, float* __restrict__ out_weight,
+    float* __restrict__ out_score) {
+  __shared__ FinalizeSmem sm;
   const int64_t q = blockIdx.x;
-  const int cnt = min(cand_cnt[q], kCandCap);
-  int32_t my_n[kCandCap / 128];
-#pragma unroll
-  for (int t = 0; t < kCandCap / 128; ++t) {
-    const int ci = tid + 128 * t;
-    my_n[t] = ci < cnt ? cand[q * kCandCap + ci] : -1;
-  }
-  if (tid < 64) qs[tid] = (tid < CK) ? __ldg(query + (int64_t)tid * query_ch_stride + q) : 0.f;
-  __syncthreads();
-  const float qq = sumsq(qs, CK);
-  const float inv_sqrt_ck = 1.0f / sqrtf((float)CK);
-#pragma unroll
-  for (int t = 0; t < kCandCap / 128; ++t) {
-    const int ci = tid + 128 * t;
-    unsigned long long key = 0ull;
-    if (my_n[t] >= 0) {
-      float kk, kq;
-      dot_row(reinterpret_cast<const float4*>(key_pm + (int64_t)my_n[t] * CK), qs, CK, kk, kq);
-      const float s = affinity_from_parts(kk, kq, qq, inv_sqrt_ck);
-      key = ((unsigned long long)float_to_ordered(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)my_n[t]);
-    }
-    keys[ci] = key;
-  }
-  __syncthreads();
-  const int take = min(top_k, cnt);
-#pragma unroll
-  for (int t = 0; t < kCandCap / 128; ++t) {
-    const int ci = tid + 128 * t;
-    if (ci < cnt) {
-      const unsigned long long mine = keys[ci];
-      int rank = 0;
-      for (int j = 0; j < cnt; ++j) rank += keys[j] > mine ? 1 : 0;  // broadcast reads; keys are unique
-      if (rank < take) sel[rank] = mine;
-    }
-  }
-  __syncthreads();
-  const float s0 = take > 0 ? ordered_to_float((uint32_t)(sel[0] >> 32)) : 0.f;
-  float e = 0.f;
-  if (tid < take) e = expf(ordered_to_float((uint32_t)(sel[tid] >> 32)) - s0);  // exp(values - values[:,0])
-  float part = e;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-  if (lane == 0) warp_sum[warp] = part;
-  __syncthreads();
-  const float total = (warp_sum[0] + warp_sum[1]) + (warp_sum[2] + warp_sum[3]);
-  if (tid < top_k) {
-    const bool live = tid < take;
-    const int64_t o = q * top_k + tid;
-    if (out_idx) out_idx[o] = live ? (int32_t)(0xffffffffu - (uint32_t)(sel[tid] & 0xffffffffull)) : -1;
-    if (out_weight) out_weight[o] = live ? e / total : 0.f;
-    if (out_score) out_score[o] = live ? ordered_to_float((uint32_t)(sel[tid] >> 32)) : -INFINITY;
-  }
+  if (only_flag != nullptr && only_flag[q] == 0) return;
+  finalize_query(sm, threadIdx.x, q, key_pm, query, query_ch_stride, CK, top_k, cand, cand_cnt[q], out_idx,
+                 out_weight, out_score, [] { __syncthreads(); });
 }
 
 }  // namespace
@@ -295,10 +207,10 @@ int launch_brute_select(const float* key_pm, const float* query, int64_t query_c
 }
 
 int launch_finalize(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_query,
-                    int top_k, const int32_t* cand, const int32_t* cand_cnt, int32_t* out_idx, float* out_weight,
-                    float* out_score, cudaStream_t st) {
-  finalize_kernel<<<(unsigned)n_query, 128, 0, st>>>(key_pm, query, query_ch_stride, CK, n_query, top_k,
-                                                                  cand, cand_cnt, out_idx, out_weight, out_score);
+                    int top_k, const int32_t* cand, const int32_t* cand_cnt, const int32_t* only_flag, int32_t* out_idx,
+                    float* out_weight, float* out_score, cudaStream_t st) {
+  finalize_kernel<<<(unsigned)n_query, 128, 0, st>>>(key_pm, query, query_ch_stride, CK, n_query, top_k, cand, cand_cnt,
+                                                     only_flag, out_idx, out_weight, out_score);
   EVAVOS_CUDA_OK(cudaGetLastError());
   return EVAVOS_OK;
 }

@@ -197,6 +197,14 @@ int evavos_memread_host(const float* mem_key, const float* query, const float* m
                         float* readout, int32_t* topk_idx, float* topk_weight, int64_t* h2d_bytes,
                         int64_t* d2h_bytes);
 
+/*
+ * Diagnostics: when enabled, evavos_memread records CUDA events between its stages on the caller's stream;
+ * evavos_stage_timing_read waits for the last call and returns ms of {candidate filter, exact-select fallback,
+ * finalize, readout}.  Not thread-safe; off by default.
+ */
+int evavos_stage_timing(int32_t enable);
+int evavos_stage_timing_read(float* ms4);
+
 /* Frees the device scratch evavos_memread_host keeps between calls. */
 int evavos_release_host_scratch(void);
 

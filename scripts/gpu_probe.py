@@ -85,6 +85,21 @@ def main():
                            iters=10, warm=2)
             line += f" | {name}: read {us:.0f} us (select only {us_sel:.0f} us)"
         print(line, flush=True)
+        if not skip_tensor:
+            import ctypes
+            lib = _lib.load()
+            lib.evavos_stage_timing(1)
+            acc = np.zeros(4)
+            reps = 20
+            for i in range(reps + 3):
+                ev.memory_read(bank, qk, 50)
+                ms = (ctypes.c_float * 4)()
+                lib.evavos_stage_timing_read(ms)
+                if i >= 3:
+                    acc += np.array(list(ms))
+            lib.evavos_stage_timing(0)
+            print(f"[{tag}] warm stage times (us): filter {acc[0] / reps * 1e3:.1f} | exact fallback {acc[1] / reps * 1e3:.1f} | "
+                  f"finalize {acc[2] / reps * 1e3:.1f} | readout {acc[3] / reps * 1e3:.1f}", flush=True)
         del bank
     p = torch.rand(3, 1, 480, 864, device=dev)
     us = timed(lambda: ev.aggregate_wbg(p, keep_bg=True), iters=50)

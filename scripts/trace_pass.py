@@ -44,6 +44,7 @@ names = ["prod_issue", "mma_ready", "mma_issued", "epi_accfull", "epi_ldtm_done"
 print("tile " + " ".join(f"{n:>13s}" for n in names))
 for i in range(0, 40):
     print(f"{i:4d} " + " ".join(f"{int(tr[r, i] - t0):13d}" for r in range(6)))
+print("kernel marks (entry, roles start, end sweep2, exit):", [int(x - t0) for x in tr[0, 56:60]])
 print("phase marks (end sweep1, after barrier1, after thresholds, after barrier2):", [int(x - t0) for x in tr[0, 60:64]])
 d = np.diff(tr[:, 8:40], axis=1)
 print("mean cycles/tile (tiles 8..40):", {n: float(d[r].mean()) for r, n in enumerate(names)})
