@@ -194,3 +194,65 @@ def test_bf16_value_bank(cv):
     out2, _ = ev.memory_read(bank2, qk2.to(dev), 50)
     _, ro2 = onp.memory_read(mk2[0].reshape(64, -1).numpy(), qk2[0].reshape(64, -1).numpy(), mv2.reshape(2, cv, -1).numpy(), 50)
     assert onp.rel_l2(out2.cpu().numpy().reshape(ro2.shape), ro2) < 1e-2
+
+
+@pytest.mark.parametrize("n_extra", [0, 1, 77, 78, 79])
+def test_small_banks_around_tile_edges(n_extra):
+    """N = 50 (== top_k), 51, 127, 128, 129: single / partial / two key tiles through the tcgen05 path."""
+    import evavos_b200 as ev
+    from evavos_b200 import _lib
+    dev = torch.device("cuda:0")
+    n = 50 + n_extra
+    g = torch.Generator().manual_seed(100 + n)
+    mk = torch.randn(1, 64, 1, 1, n, generator=g)          # one "frame" of n positions
+    qk = torch.randn(1, 64, 3, 1, 45, generator=g)          # 3 query frames of 45 positions
+    mv = torch.randn(2, 40, 1, 1, n, generator=g)
+    bank = ev.MemoryBank.from_tensors(mk.to(dev), mv.to(dev))
+    s64 = onp.affinity_scores(mk[0].reshape(64, -1).numpy(), qk[0].reshape(64, -1).numpy())
+    tk = onp.topk_softmax(s64, 50)
+    ro = onp.readout(tk.idx, tk.weight, mv.reshape(2, 40, -1).numpy())
+    for path in (_lib.PATH_TENSOR, _lib.PATH_SIMT):
+        out, aff = ev.memory_read(bank, qk.to(dev), 50, want_topk=True, path=path)
+        exact, tie, bad, _ = onp.compare_topk(aff.idx.cpu().numpy(), s64, 50, TIE_TOL)
+        assert bad == 0
+        assert onp.rel_l2(out.cpu().numpy().reshape(ro.shape), ro) < (1e-5 if tie == 0 else 1e-3)
+
+
+@pytest.mark.parametrize("top_k", [1, 7, 128])
+def test_other_top_k(top_k):
+    import evavos_b200 as ev
+    from evavos_b200 import _lib
+    dev = torch.device("cuda:0")
+    mk, qk, mv = synth(300 + top_k, 64, 128, 3, 10, 13, 1)
+    bank = ev.MemoryBank.from_tensors(mk.to(dev), mv.to(dev))
+    s64 = onp.affinity_scores(mk[0].reshape(64, -1).numpy(), qk[0].reshape(64, -1).numpy())
+    tk = onp.topk_softmax(s64, top_k)
+    ro = onp.readout(tk.idx, tk.weight, mv.reshape(1, 128, -1).numpy())
+    for path in (_lib.PATH_TENSOR, _lib.PATH_SIMT):
+        out, aff = ev.memory_read(bank, qk.to(dev), top_k, want_topk=True, path=path)
+        exact, tie, bad, _ = onp.compare_topk(aff.idx.cpu().numpy(), s64, top_k, TIE_TOL)
+        assert bad == 0
+        assert onp.rel_l2(out.cpu().numpy().reshape(ro.shape), ro) < (1e-5 if tie == 0 else 1e-3)
+
+
+def test_more_query_tiles_than_sms():
+    """n_query > 128 * SM count: the cooperative filter runs in several waves of query tiles."""
+    import evavos_b200 as ev
+    dev = torch.device("cuda:0")
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    nq = 128 * n_sm + 200
+    g = torch.Generator().manual_seed(9)
+    mk = torch.randn(1, 64, 2, 10, 10, generator=g)
+    mv = torch.randn(1, 16, 2, 10, 10, generator=g)
+    qk = torch.randn(1, 64, 1, nq, generator=g)
+    bank = ev.MemoryBank.from_tensors(mk.to(dev), mv.to(dev))
+    out, aff = ev.memory_read(bank, qk.to(dev), 50, want_topk=True)
+    s64 = onp.affinity_scores(mk[0].reshape(64, -1).numpy(), qk[0].reshape(64, -1).numpy())
+    idx = aff.idx.cpu().numpy()
+    rng = np.random.default_rng(1)
+    sample = np.concatenate([rng.choice(nq, 300, replace=False), np.arange(nq - 200, nq)])
+    exact, tie, bad, _ = onp.compare_topk(idx[sample], s64[:, sample], 50, TIE_TOL)
+    assert bad == 0
+    tk = onp.topk_softmax(s64[:, sample], 50)
+    ro = onp.readout(tk.idx, tk.weight, mv.reshape(1, 16, -1).numpy())
+    assert onp.rel_l2(out.cpu().numpy().reshape(1, 16, nq)[:, :, sample], ro) < 1e-3
