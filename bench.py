@@ -8,8 +8,12 @@ Workload (BASELINE.json configs[1]): DAVIS-17 480p, 30x54 feature map, 3 objects
 
  * value  - whole-job query-frames/s with the bank resident in HBM (CUDA events, max over ranks).
             Four banks (each > L2 together) are rotated so no step finds its inputs in L2.
- * e2e    - the same read through evavos_memread_host with pinned HOST buffers in the reference
-            layout: H2D of keys/query/values, shadow build, read, D2H of the readout, every step.
+ * e2e    - the same step through the public API with pinned HOST buffers, synchronised every step.  The bank
+            is engine state (exactly as the reference keeps its bank resident in host memory between frames); a
+            step's inputs are the frame's query key, the decoder probabilities and - every mem_freq-th frame -
+            one new memory frame (H2D + in-place append, inference_core.py:174-177); its result is the readout
+            and the aggregated probabilities (D2H).  `e2e_full_upload` is the stateless variant
+            (evavos_memread_host: the whole bank crosses PCIe every step).
  * roofline - the dominant kernel (sparse readout, HBM-bound), timed with CUDA events inside the
             timed region; algorithmic bytes = s*K*CV*min(N, k*HW) + 4*K*CV*HW + 8*k*HW.
  * cpu_baseline / --impl reference - oracle/torch_port.py (op-for-op port of the reference's dense
@@ -315,6 +319,42 @@ def run_ours(args, cfg, rank, world, local_rank):
     h_agg = torch.empty((k + 1, 1, h * 16, w * 16), dtype=torch.float32).pin_memory()
     e2e_steps = max(3, min(args.steps, 20))
 
+    # streaming e2e: the bank persists; per step H2D = query (+ 1/mem_freq of a new memory frame) + probabilities
+    mem_freq = 5
+    s_bank = ev.MemoryBank(k, ck, cv, h, w, t, dev)              # reference-layout tensors + shadow, like do_pass
+    s_bank.write_frames(0, mk.to(dev), mv.to(dev))
+    h_q = [torch.randn(1, ck, h, w, generator=torch.Generator().manual_seed(seed + 7 * j)).pin_memory() for j in range(4)]
+    h_newk = mk[:, :, 0].contiguous().pin_memory()
+    h_newv = mv[:, :, 0:1].contiguous().pin_memory()
+    s_steps = max(10, min(args.steps, 100))
+
+    def stream_step(i):
+        q = h_q[i % 4].to(dev, non_blocking=True)
+        if i % mem_freq == 0:
+            s_bank.write_frames((i // mem_freq) % t, h_newk.to(dev, non_blocking=True), h_newv.to(dev, non_blocking=True))
+        out, _ = ev.memory_read(s_bank, q, TOP_K)
+        agg = ev.aggregate_wbg(h_prob.to(dev, non_blocking=True), keep_bg=True)
+        h_out.copy_(out.view(k, cv, hw), non_blocking=True)
+        h_agg.copy_(agg, non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    s_h2d = h_q[0].numel() * 4 + (h_newk.numel() + h_newv.numel()) * 4 // mem_freq + h_prob.numel() * 4
+    s_d2h = h_out.numel() * 4 + h_agg.numel() * 4
+    for i in range(5):
+        stream_step(i)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    c0 = time.perf_counter()
+    for i in range(s_steps):
+        stream_step(i)
+    torch.cuda.synchronize(dev)
+    stream_s = time.perf_counter() - c0
+    if dist:
+        tm = torch.tensor([stream_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        stream_s = float(tm.item())
+
     def e2e_step():
         h2d, d2h = memory_read_host(h_mk, h_qk, h_mv, TOP_K, out=h_out)
         p = h_prob.to(dev, non_blocking=True)
@@ -356,9 +396,14 @@ def run_ours(args, cfg, rank, world, local_rank):
                    "l2": f"{N_BANKS} rotating banks, {N_BANKS * (4 * k * cv * n_pos + 4 * ck * n_pos) / 1e6:.0f} MB of inputs > 126 MB L2",
                    "filter": "tcgen05 bf16 candidate filter + exact fp32 rescoring", "parallelism": f"independent videos x{world}"},
         "clocks": clocks,
-        "e2e": {"value": world * e2e_steps / e2e_s, "unit": "query-frames/s", "h2d_bytes_per_step": int(h2d_b),
-                "d2h_bytes_per_step": int(d2h_b), "steps": e2e_steps,
-                "note": "evavos_memread_host: full bank + query H2D from pinned memory, shadow build, read, readout D2H, every step"},
+        "e2e": {"value": world * s_steps / stream_s, "unit": "query-frames/s", "h2d_bytes_per_step": int(s_h2d),
+                "d2h_bytes_per_step": int(s_d2h), "steps": s_steps,
+                "note": "public API, pinned host buffers, synchronised every step: H2D query key + decoder probabilities + "
+                        "(every 5th step) one new memory frame appended in place; D2H readout + aggregated probabilities; "
+                        "the bank itself is engine state, as in the reference"},
+        "e2e_full_upload": {"value": world * e2e_steps / e2e_s, "unit": "query-frames/s", "h2d_bytes_per_step": int(h2d_b),
+                            "d2h_bytes_per_step": int(d2h_b), "steps": e2e_steps,
+                            "note": "evavos_memread_host: stateless, the whole bank + query H2D, shadow build, read, D2H, every step"},
         "gpu_launches": KERNELS_PER_STEP * args.steps,
         "roofline": {"bound": "hbm", "kernel": "readout_f32_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
