@@ -57,18 +57,39 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(
   for (int o = 16; o > 0; o >>= 1) live += __shfl_xor_sync(0xffffffffu, live, o);
   __syncwarp();
   const int take = min(top_k, live);
-  for (int j = 0; j < take; ++j) {
-    unsigned long long best = 0ull;
-    for (int c = lane; c < n_cand; c += 32) best = keys[c] > best ? keys[c] : best;
+  if (n_shards <= 32) {
+    // Every shard's list arrives best-first (finalize_kernel's order), so the global order is a tournament of the
+    // list heads: lane s owns list s, one warp-wide max and one pointer advance per output.
+    int ptr = 0;
+    unsigned long long head = lane < n_shards ? keys[lane * per_shard] : 0ull;
+    for (int j = 0; j < take; ++j) {
+      unsigned long long best = head;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-      best = other > best ? other : best;
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+      }
+      if (head == best && best != 0ull) {  // keys are unique: exactly one lane advances
+        ++ptr;
+        head = ptr < per_shard ? keys[lane * per_shard + ptr] : 0ull;
+      }
+      if (lane == 0) sel[j] = best;
     }
-    for (int c = lane; c < n_cand; c += 32)
-      if (keys[c] == best) keys[c] = 0ull;  // positions are unique across shards
-    if (lane == 0) sel[j] = best;
     __syncwarp();
+  } else {
+    for (int j = 0; j < take; ++j) {
+      unsigned long long best = 0ull;
+      for (int c = lane; c < n_cand; c += 32) best = keys[c] > best ? keys[c] : best;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+      }
+      for (int c = lane; c < n_cand; c += 32)
+        if (keys[c] == best) keys[c] = 0ull;  // positions are unique across shards
+      if (lane == 0) sel[j] = best;
+      __syncwarp();
+    }
   }
   const float s0 = take > 0 ? ordered_to_float((uint32_t)(sel[0] >> 32)) : 0.f;
   float e[EVAVOS_MAX_TOPK / 32];

@@ -163,7 +163,8 @@ int evavos_aggregate_wbg(const float* prob, float* out, int32_t K, int64_t npix,
 
 /*
  * Merge step of the memory-axis sharded read.  cand_idx/cand_score: (n_query, n_cand)
- * all-gathered per-shard top-k (GLOBAL positions, -1 = empty).  Selects the global top_k
+ * all-gathered per-shard top-k (GLOBAL positions, -1 = empty), shard-major: n_cand / n_shards entries per
+ * shard, each shard's entries best-first as evavos_memread emits them.  Selects the global top_k
  * per query (score descending, position ascending on ties), computes softmax weights with
  * the global max and denominator, and emits
  *   out_idx/out_weight/out_score (n_query, top_k): the merged result (any may be NULL)
