@@ -5,6 +5,13 @@
 
 namespace evavos {
 
+#ifdef EVAVOS_TRACE
+static __device__ int g_fin_skip = 0;   // timing experiments only: 1 = no row loads, 2 = no rank loop, 4 = no |q|^2 loop
+#define EVAVOS_FIN_SKIP(bit) (g_fin_skip & (bit))
+#else
+#define EVAVOS_FIN_SKIP(bit) 0
+#endif
+
 // kk += |k|^2, kq += k.q over CK channels, channel order 0..CK-1, one FMA per term.
 __device__ __forceinline__ void dot_row(const float4* __restrict__ krow, const float* __restrict__ q, int CK,
                                         float& kk, float& kq) {
@@ -67,15 +74,15 @@ __device__ __forceinline__ void finalize_query(FinalizeSmem& sm, int tid, int64_
   }
   if (tid < 64) sm.qs[tid] = (tid < CK) ? __ldg(query + (int64_t)tid * query_ch_stride + q) : 0.f;
   sync();
-  const float qq = sumsq(sm.qs, CK);
+  const float qq = EVAVOS_FIN_SKIP(4) ? 1.f : sumsq(sm.qs, CK);
   const float inv_sqrt_ck = 1.0f / sqrtf((float)CK);
 #pragma unroll
   for (int t = 0; t < kCandCap / 128; ++t) {
     const int ci = tid + 128 * t;
     unsigned long long key = 0ull;
     if (my_n[t] >= 0) {
-      float kk, kq;
-      dot_row(reinterpret_cast<const float4*>(key_pm + (int64_t)my_n[t] * CK), sm.qs, CK, kk, kq);
+      float kk = (float)my_n[t], kq = 1.f;
+      if (!EVAVOS_FIN_SKIP(1)) dot_row(reinterpret_cast<const float4*>(key_pm + (int64_t)my_n[t] * CK), sm.qs, CK, kk, kq);
       const float s = affinity_from_parts(kk, kq, qq, inv_sqrt_ck);
       key = ((unsigned long long)float_to_ordered(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)my_n[t]);
     }
@@ -89,7 +96,9 @@ __device__ __forceinline__ void finalize_query(FinalizeSmem& sm, int tid, int64_
     if (ci < cnt) {
       const unsigned long long mine = sm.keys[ci];
       int rank = 0;
-      for (int j = 0; j < cnt; ++j) rank += sm.keys[j] > mine ? 1 : 0;  // broadcast reads; keys are unique
+      if (EVAVOS_FIN_SKIP(2)) rank = ci;
+      else
+        for (int j = 0; j < cnt; ++j) rank += sm.keys[j] > mine ? 1 : 0;  // broadcast reads; keys are unique
       if (rank < take) sm.sel[rank] = mine;
     }
   }

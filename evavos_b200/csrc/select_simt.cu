@@ -16,6 +16,10 @@
 
 namespace evavos {
 
+#ifdef EVAVOS_TRACE
+extern "C" int evavos_debug_fin_skip(int v) { return (int)cudaMemcpyToSymbol(g_fin_skip, &v, sizeof(int)); }
+#endif
+
 namespace {
 
 constexpr int kBruteQ = 4;  // queries per CTA pass
