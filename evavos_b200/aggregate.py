@@ -25,3 +25,22 @@ def aggregate_wbg(prob: torch.Tensor, keep_bg: bool = False, hard: bool = False)
         _lib.check(lib.evavos_aggregate_wbg(p.data_ptr(), out.data_ptr(), k, npix, int(bool(keep_bg)), int(bool(hard)),
                                             _lib.current_stream_ptr(prob.device)))
     return out
+
+
+def argmax_unpad(prob: torch.Tensor, pad, h: int, w: int):
+    """prob (C,T,1,nh,nw) fp32 -> (masks uint8 (T,1,nh,nw), unpadded uint8 (T,h,w)), one kernel for all frames.
+
+    ``pad`` is the (lw, uw, lh, uh) tuple of pad_divide_by (mivos/tensor_util.py:62-80); replaces
+    inference_core.py:247-257.
+    """
+    lib = _lib.load()
+    if not prob.is_cuda:
+        raise RuntimeError("argmax_unpad: CUDA tensor required (no CPU path in evavos_b200)")
+    c, t, _, nh, nw = prob.shape
+    p = prob.to(torch.float32).contiguous()
+    masks = torch.empty((t, 1, nh, nw), dtype=torch.uint8, device=prob.device)
+    out = torch.empty((t, h, w), dtype=torch.uint8, device=prob.device)
+    with torch.cuda.device(prob.device):
+        _lib.check(lib.evavos_argmax_unpad(p.data_ptr(), c, t, nh, nw, masks.data_ptr(), out.data_ptr(), int(pad[2]),
+                                           int(pad[0]), int(h), int(w), _lib.current_stream_ptr(prob.device)))
+    return masks, out

@@ -287,6 +287,16 @@ int evavos_aggregate_wbg(const float* prob, float* out, int32_t K, int64_t npix,
   return launch_aggregate(prob, out, K, npix, keep_bg, hard, (cudaStream_t)stream);
 }
 
+int evavos_argmax_unpad(const float* prob, int32_t C, int64_t T, int32_t nh, int32_t nw, uint8_t* masks, uint8_t* out,
+                        int32_t pad_top, int32_t pad_left, int32_t h, int32_t w, evavos_stream_t stream) {
+  if (!prob || C <= 0 || C > 255 || T < 0 || nh <= 0 || nw <= 0 || (!masks && !out) ||
+      (out && (pad_top < 0 || pad_left < 0 || h <= 0 || w <= 0 || pad_top + h > nh || pad_left + w > nw))) {
+    set_error("argmax_unpad: bad arguments");
+    return EVAVOS_ERR_INVALID;
+  }
+  return launch_argmax_unpad(prob, C, T, nh, nw, masks, out, pad_top, pad_left, h, w, (cudaStream_t)stream);
+}
+
 int evavos_topk_merge(const int32_t* cand_idx, const float* cand_score, int64_t n_query, int32_t n_cand,
                       int32_t top_k, int32_t shard, int32_t n_shards, int64_t pos_per_frame, int32_t* out_idx,
                       float* out_weight, float* out_score, int32_t* local_idx, evavos_stream_t stream) {

@@ -101,6 +101,8 @@ int launch_affinity_dense(const int32_t* idx, const float* weight, int64_t n_que
                           float* dense, cudaStream_t st);
 int launch_aggregate(const float* prob, float* out, int K, int64_t npix, int keep_bg, int hard,
                      cudaStream_t st);
+int launch_argmax_unpad(const float* prob, int C, int64_t T, int nh, int nw, uint8_t* masks, uint8_t* out,
+                        int pad_top, int pad_left, int h, int w, cudaStream_t st);
 int launch_topk_merge(const int32_t* cand_idx, const float* cand_score, int64_t n_query, int n_cand, int top_k,
                       int shard, int n_shards, int64_t pos_per_frame, int32_t* out_idx, float* out_weight,
                       float* out_score, int32_t* local_idx, int gathered, cudaStream_t st);

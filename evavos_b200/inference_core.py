@@ -22,7 +22,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .aggregate import aggregate_wbg
+from .aggregate import aggregate_wbg, argmax_unpad
 from .memory_bank import MemoryBank
 from .memory_reader import EvalMemoryReader
 from .tensor_util import pad_divide_by
@@ -223,12 +223,7 @@ class InferenceCore:
         self.do_pass(key_k, key_v, idx, True)
         self.do_pass(key_k, key_v, idx, False)
 
-        # all frames in one launch (the reference loops T argmax calls, :247-248)
-        self.masks = torch.argmax(self.prob, dim=0).to(torch.uint8)
-        out_masks = self.masks
-        if self.pad[2] + self.pad[3] > 0:
-            out_masks = out_masks[:, :, self.pad[2]:out_masks.shape[2] - self.pad[3], :]
-        if self.pad[0] + self.pad[1] > 0:
-            out_masks = out_masks[:, :, :, self.pad[0]:out_masks.shape[3] - self.pad[1]]
-        self.np_masks = (out_masks.detach().cpu().numpy()[:, 0]).astype(np.uint8)
+        # all frames, argmax + un-padding in one kernel (the reference loops T argmax calls and slices, :247-257)
+        self.masks, unpadded = argmax_unpad(self.prob, self.pad, self.h, self.w)
+        self.np_masks = unpadded.cpu().numpy()
         return self.np_masks

@@ -16,6 +16,8 @@
  *                           replace the in-place bank append and the certain-memory
  *                           copy of InferenceCore.do_pass (mivos/inference_core.py:150-155,
  *                           174-177) and the torch.cat growth in interact (:235-240).
+ *   evavos_argmax_unpad     replaces the per-frame argmax + un-padding at the end of interact
+ *                           (mivos/inference_core.py:247-257).
  *   evavos_topk_merge       the exchange step of the memory-axis sharded read
  *                           (no reference counterpart).
  *   evavos_memread_host     the same read with HOST buffers in the reference layout
@@ -160,6 +162,15 @@ int evavos_affinity_dense(const int32_t* idx, const float* weight, int64_t n_que
 /* Soft aggregation: prob (K, npix) fp32 -> out (K+1, npix) if keep_bg else (K, npix). */
 int evavos_aggregate_wbg(const float* prob, float* out, int32_t K, int64_t npix, int32_t keep_bg,
                          int32_t hard, evavos_stream_t stream);
+
+/*
+ * Hard masks of all frames in one pass (replaces the per-frame torch.argmax loop, the un-padding slices and the
+ * contiguous copy of mivos/inference_core.py:247-257).  prob: (C, T, nh, nw) fp32, C <= 255.
+ *   masks: (T, nh, nw) uint8 channel argmax (first maximal channel), or NULL
+ *   out:   (T, h, w)   uint8 the same without the padding (rows pad_top.., columns pad_left..), or NULL
+ */
+int evavos_argmax_unpad(const float* prob, int32_t C, int64_t T, int32_t nh, int32_t nw, uint8_t* masks, uint8_t* out,
+                        int32_t pad_top, int32_t pad_left, int32_t h, int32_t w, evavos_stream_t stream);
 
 /*
  * Merge step of the memory-axis sharded read.  cand_idx/cand_score: (n_query, n_cand)

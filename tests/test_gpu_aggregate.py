@@ -41,3 +41,22 @@ def test_aggregate_vs_oracle_full_size(k):
         assert np.abs(out.sum(0) - 1).max() < 1e-5
         out2 = ev.aggregate_wbg(p.cuda(), keep_bg=False).cpu().numpy()
         assert np.array_equal(out2, out[1:])
+
+
+@pytest.mark.parametrize("shape,hw", [((3, 7, 1, 48, 64), (41, 57)), ((2, 5, 1, 32, 48), (32, 48)), ((4, 3, 1, 34, 50), (30, 47))])
+def test_argmax_unpad_matches_torch(shape, hw):
+    """Fused channel argmax + un-padding == torch.argmax per frame + slicing (inference_core.py:247-257)."""
+    import evavos_b200 as ev
+    from evavos_b200.tensor_util import pad_divide_by
+    c, t, _, nh, nw = shape
+    h, w = hw
+    g = torch.Generator().manual_seed(c * 100 + t)
+    prob = torch.rand(shape, generator=g)
+    prob[:, :, :, ::3, ::5] = 0.25                      # exact ties: the first maximal channel must win
+    lh, lw = (nh - h) // 2, (nw - w) // 2
+    pad = (lw, nw - w - lw, lh, nh - h - lh)
+    masks, out = ev.argmax_unpad(prob.cuda(), pad, h, w)
+    ref = torch.argmax(prob, dim=0).to(torch.uint8)      # (t,1,nh,nw)
+    assert torch.equal(masks.cpu(), ref)
+    assert torch.equal(out.cpu(), ref[:, 0, lh:lh + h, lw:lw + w])
+    assert out.is_contiguous() and out.dtype == torch.uint8
