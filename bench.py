@@ -43,6 +43,7 @@ WORKLOADS = {
     "cfg1": (64, 512, 5, 30, 54, 1, 1235, "DAVIS-17 480p (30x54), 1 object, 5-frame bank"),
     "cfg2": (64, 512, 20, 30, 54, 3, 1236, "DAVIS-17 480p (30x54), 3 objects, 20-frame bank, top-50 readout + soft aggregation"),
     "cfg4": (64, 512, 200, 30, 54, 1, 1238, "MOSE-style long video 480p, 1 object, 200-frame bank (unsharded)"),
+    "cfg3": (64, 512, 32, 30, 54, 1, 1237, "independent synthetic 480p videos (32 frames, 1 object), full key/value encode + memory read + decode"),
     "cfg5": (64, 512, 50, 68, 120, 5, 1239, "1080p-equivalent feature map (68x120), 5 objects, 50-frame bank, bf16 value bank"),
 }
 TOP_K = 50
@@ -305,6 +306,50 @@ def run_cfg5(args, cfg, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def run_cfg3(args, cfg, rank, world, local_rank):
+    """BASELINE.json configs[2]: end-to-end InferenceCore.interact on independent synthetic 480p videos, one process
+    per GPU, no collective.  A step is one video (mask on frame 0, propagated to the other 31 frames); the conv
+    encoders/decoder (PyTorch/cuDNN, random weights) dominate - the memory read is a small share here."""
+    import evavos_b200 as ev
+    from evavos_b200.networks import seeded_init
+    _, _, t, _, _, k, seed, desc = cfg
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    torch.set_grad_enabled(False)
+    prop, fuse = ev.PropagationNetwork().eval().to(dev), ev.FusionNet().eval().to(dev)
+    seeded_init(prop, 1001)
+    seeded_init(fuse, 1002)
+    h, w = 480, 854
+    g = torch.Generator().manual_seed(seed + rank)
+    videos = [torch.rand(1, t, 3, h, w, generator=g) for _ in range(2)]
+    mask = (torch.rand(1, 1, h // 8, (w + 7) // 8, generator=g) > 0.6).float()
+    mask = mask.repeat_interleave(8, 2).repeat_interleave(8, 3)[:, :, :h, :w]
+
+    def one_video(i):
+        proc = ev.InferenceCore(prop, fuse, videos[i % 2], k, device=dev)
+        return proc.interact(mask, 0)
+
+    for i in range(max(1, min(args.warmup, 2))):
+        one_video(i)
+    torch.cuda.synchronize(dev)
+    c0 = time.perf_counter()
+    for i in range(args.steps):
+        out = one_video(i)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - c0
+    if rank != 0:
+        return
+    line = {
+        "metric": "propagated frames/sec (end-to-end interact)", "value": world * args.steps * (t - 1) / dt, "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (cuDNN TF32 convolutions)",
+        "data": "synthetic", "config": {"workload": args.workload + ": " + desc, "frames": t, "image": [h, w], "mem_freq": 5,
+                                         "note": "wall clock incl. H2D of the video and D2H of the masks; random weights"},
+        "mask_shape": list(out.shape),
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_ours(args, cfg, rank, world, local_rank):
     import evavos_b200 as ev
     from evavos_b200 import _lib
@@ -516,6 +561,8 @@ def main():
         run_sharded(args, cfg, rank, world, local_rank)
     elif args.workload == "cfg5":
         run_cfg5(args, cfg, rank, world, local_rank)
+    elif args.workload == "cfg3":
+        run_cfg3(args, cfg, rank, world, local_rank)
     else:
         run_ours(args, cfg, rank, world, local_rank)
 
