@@ -39,6 +39,12 @@ __device__ long long g_trace[6][64];
 #define EVAVOS_TR(row, i) do { } while (0)
 #endif
 
+// Compile-time timing experiments (-DEVAVOS_EXP=bits; results are wrong while a bit is set):
+// 1 = the epilogue skips the TMEM load, 2 = skips its math.
+#ifndef EVAVOS_EXP
+#define EVAVOS_EXP 0
+#endif
+
 namespace {
 
 constexpr int kStages = 8;
@@ -48,7 +54,13 @@ constexpr int kThreads = 640;
 constexpr int kEpiThreads = 512;
 constexpr int kProducers = 4;   // TMA-issuing lanes of warp 0 (kStages % kProducers == 0)
 constexpr int kCols = 32;       // accumulator columns per epilogue thread
-constexpr int kPend = 16;       // staged hit groups per epilogue thread (flushed when more than half full)
+// Scores per staged hit group (sweep 2 tests one maximum per group).  Measured, filter time in us for 4 | 8:
+// cfg2 (32 k positions, a hit in 23 % | 40 % of the warp-groups) 43.8 | 52.7, cfg4 (324 k positions) 168.8 | 162.9.
+#ifndef EVAVOS_GROUP
+#define EVAVOS_GROUP 4
+#endif
+constexpr int kGroup = EVAVOS_GROUP;
+constexpr int kPend = 8 + kCols / kGroup;  // staged hit groups per epilogue thread (flushed when more than 8 wait)
 constexpr int kBarBytes = 256;
 constexpr int kSmemBytes = kTileBytes * kStages + kBarBytes + 1024;
 
@@ -83,6 +95,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// One lane of a converged warp (the tcgen05 issue idiom: the branch stays warp-uniform for the compiler).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -161,7 +179,7 @@ struct PassParams {
   float* tau;
   int32_t* cand;
   int32_t* cand_cnt;
-  float4* pend_score;   // [grid][kPend][kEpiThreads] scores of staged hit groups (pass 2)
+  float4* pend_score;   // [grid][kPend * kGroup / 4][kEpiThreads] scores of staged hit groups (sweep 2)
   int32_t* pend_pos;    // [grid][kPend][kEpiThreads] first position of each staged group
   const float* key_maxnorm;
   unsigned int* grid_counter;  // one counter per query tile of the launch, zeroed before every launch
@@ -169,21 +187,20 @@ struct PassParams {
   int top_k;
 };
 
-// Pass 2 stages every group of 4 adjacent scores whose maximum reaches the threshold (scores + first
-// position, two predicated stores, no branch) in a private strip of the workspace; the strip is resolved
-// into the query's candidate list out of line.  Hits are rare: about top_k + margin per query over the
-// whole bank.
+// Sweep 2 stages every group of kGroup adjacent scores whose maximum reaches the threshold (scores + first
+// position) in a private strip of the workspace; the strip is resolved into the query's candidate list out of
+// line.  Hits are rare: about top_k + margin per query over the whole bank.
 __device__ __noinline__ void flush_pending(const float4* ps, const int32_t* pp, int n, float thr, int32_t* cand,
                                            int32_t* cand_cnt, int64_t q) {
   int hits = 0;
-  for (int e = 0; e < n; ++e) {
+  for (int e = 0; e < n * (kGroup / 4); ++e) {
     const float4 s = ps[e * kEpiThreads];
     hits += (s.x >= thr) + (s.y >= thr) + (s.z >= thr) + (s.w >= thr);
   }
   int at = atomicAdd(cand_cnt + q, hits);
-  for (int e = 0; e < n; ++e) {
+  for (int e = 0; e < n * (kGroup / 4); ++e) {
     const float4 s = ps[e * kEpiThreads];
-    const int32_t n0 = pp[e * kEpiThreads];
+    const int32_t n0 = pp[(e / (kGroup / 4)) * kEpiThreads] + 4 * (e % (kGroup / 4));
     const float v[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -201,21 +218,27 @@ __device__ __forceinline__ void consume_tile(const float* v, float* cmax, float 
                                              float4* ps, int32_t* pp, int& pending) {
   // valid: number of in-range columns among this thread's kCols (only read when PARTIAL)
   if constexpr (PASS == 1) {
+    // kCols / 2 classes per call, two columns each: one 3-input max per two scores
 #pragma unroll
-    for (int j = 0; j < kCols; ++j) {
-      const float s = (PARTIAL && j >= valid) ? kEmptyNh : v[j];
-      cmax[j] = fmaxf(cmax[j], s);
+    for (int j = 0; j < kCols / 2; ++j) {
+      const float s0 = (PARTIAL && j >= valid) ? kEmptyNh : v[j];
+      const float s1 = (PARTIAL && j + kCols / 2 >= valid) ? kEmptyNh : v[j + kCols / 2];
+      cmax[j] = fmaxf(fmaxf(cmax[j], s0), s1);
     }
   } else {
 #pragma unroll
-    for (int j4 = 0; j4 < kCols / 4; ++j4) {
-      float s4[4];
+    for (int g = 0; g < kCols / kGroup; ++g) {
+      float sg[kGroup];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) s4[e] = (PARTIAL && j4 * 4 + e >= valid) ? kEmptyNh : v[j4 * 4 + e];
-      const float m4 = fmaxf(fmaxf(s4[0], s4[1]), fmaxf(s4[2], s4[3]));
-      if (m4 >= thr) {  // if-converted: two predicated stores and an increment
-        ps[pending * kEpiThreads] = make_float4(s4[0], s4[1], s4[2], s4[3]);
-        pp[pending * kEpiThreads] = n_first + j4 * 4;
+      for (int e = 0; e < kGroup; ++e) sg[e] = (PARTIAL && g * kGroup + e >= valid) ? -INFINITY : v[g * kGroup + e];
+      float m = sg[0];
+#pragma unroll
+      for (int e = 1; e < kGroup; ++e) m = fmaxf(m, sg[e]);
+      if (m >= thr) {
+#pragma unroll
+        for (int h = 0; h < kGroup / 4; ++h)
+          ps[(pending * (kGroup / 4) + h) * kEpiThreads] = make_float4(sg[4 * h], sg[4 * h + 1], sg[4 * h + 2], sg[4 * h + 3]);
+        pp[pending * kEpiThreads] = n_first + g * kGroup;
         ++pending;
       }
     }
@@ -326,7 +349,10 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
       reinterpret_cast<volatile uint32_t*>(base_ptr + kTileBytes * kStages + 16 * kStages + 16 * kAccStages);
 
   if (threadIdx.x == 0) EVAVOS_TR(0, 56);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform, keeps everything derived from it
+  // (loop counters, stage addresses, UMMA descriptors) in uniform registers and issues the five tcgen05.mma of a
+  // tile back to back instead of wrapping each in an R2UR broadcast loop (~95 -> ~40 clk of issue per MMA)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int m_tile = p.m_tile0 + blockIdx.x % p.n_mtiles;
   const int chunk = blockIdx.x / p.n_mtiles;
   const int t0 = (int)(((int64_t)chunk * p.n_ktiles) / p.n_chunks);
@@ -362,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
 
   // Query operand: thread r of the first epilogue warpgroup converts query row q0 + r (64 channels, read in the
   // caller's layout, coalesced across the warp) to bf16 pairs and stores them, followed by the (1, 1, 1, 0...)
@@ -419,7 +445,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
       mbar_wait(bar_full + 8 * s, (uint32_t)((i / kStages) & 1));
       mbar_wait(bar_acc_empty + 8 * a, (uint32_t)(((i / kAccStages) & 1) ^ 1));
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         EVAVOS_TR(1, i);
         const uint32_t st = stage0 + s * kTileBytes;
         const uint64_t bdesc0 = make_desc(st, 1024, kLayoutSw128);
@@ -450,8 +476,12 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
       mbar_wait(bar_acc_full + 8 * a, (uint32_t)((i / kAccStages) & 1));
       tc_fence_after();
       if (threadIdx.x == 128) EVAVOS_TR(3, i);
-      tmem_ld32(lane_addr + (uint32_t)(a * 128 + col0), v);
-      tmem_ld_wait();
+      if constexpr (!(EVAVOS_EXP & 1)) {
+        tmem_ld32(lane_addr + (uint32_t)(a * 128 + col0), v);
+        tmem_ld_wait();
+      } else {
+        for (int j = 0; j < kCols; ++j) v[j] = kEmptyNh;
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty + 8 * a);  // registers hold the tile: release the TMEM stage
@@ -463,18 +493,28 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
       float cmax[kCols];
 #pragma unroll
       for (int j = 0; j < kCols; ++j) cmax[j] = kEmptyNh;
-      for (int i = 0; i < n_tiles; ++i) {
+      // Column classes: (tile parity, column mod 16) per thread, i.e. 2 x 4 x 16 = 128 per query
+      // and chunk - any partition of the positions into classes gives a valid bound, this one costs one FMNMX3
+      // per two scores.  cmax[0..15] collects the even tiles, cmax[16..31] the odd ones.
+      auto tile_max = [&](int i, float* cm) {
         float v[kCols];
         load_tile(i, v);
         const int64_t n0 = (int64_t)tile_of(i) * kTilePos + col0;
         int pending = 0;
-        if (n0 + kCols > p.n_pos) {
+        if constexpr ((EVAVOS_EXP & 2) != 0) {
+        } else if (n0 + kCols > p.n_pos) {
           const int valid = (int)max((int64_t)0, p.n_pos - n0);
-          consume_tile<1, true>(v, cmax, 0.f, (int32_t)n0, valid, nullptr, nullptr, pending);
+          consume_tile<1, true>(v, cm, 0.f, (int32_t)n0, valid, nullptr, nullptr, pending);
         } else {
-          consume_tile<1, false>(v, cmax, 0.f, (int32_t)n0, kCols, nullptr, nullptr, pending);
+          consume_tile<1, false>(v, cm, 0.f, (int32_t)n0, kCols, nullptr, nullptr, pending);
         }
         if (threadIdx.x == 128) EVAVOS_TR(5, i);
+      };
+      int i = 0;
+      if (t0 & 1) tile_max(i++, cmax + kCols / 2);  // parity of the tile's index in the bank, not in the chunk
+      for (; i < n_tiles; i += 2) {
+        tile_max(i, cmax);
+        if (i + 1 < n_tiles) tile_max(i + 1, cmax + kCols / 2);
       }
       float4* dst = reinterpret_cast<float4*>(p.class_max + ((int64_t)chunk * p.nq_pad + q) * 128 + col0);
 #pragma unroll
@@ -501,7 +541,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
     {
       float thr = INFINITY;
       if (q < p.n_query) thr = __ldcg(p.tau + q);
-      float4* ps = p.pend_score + (int64_t)blockIdx.x * kPend * kEpiThreads + et;
+      float4* ps = p.pend_score + (int64_t)blockIdx.x * (kPend * kGroup / 4) * kEpiThreads + et;
       int32_t* pp = p.pend_pos + (int64_t)blockIdx.x * kPend * kEpiThreads + et;
       int pending = 0;
       float unused[1];
@@ -509,13 +549,14 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
         float v[kCols];
         load_tile(i, v);
         const int64_t n0 = (int64_t)tile_of(i) * kTilePos + col0;
-        if (n0 + kCols > p.n_pos) {
+        if constexpr ((EVAVOS_EXP & 2) != 0) {
+        } else if (n0 + kCols > p.n_pos) {
           const int valid = (int)max((int64_t)0, p.n_pos - n0);
           consume_tile<2, true>(v, unused, thr, (int32_t)n0, valid, ps, pp, pending);
         } else {
           consume_tile<2, false>(v, unused, thr, (int32_t)n0, kCols, ps, pp, pending);
         }
-        if (pending > kPend - kCols / 4) {  // the next tile stages at most kCols / 4 groups
+        if (pending > kPend - kCols / kGroup) {  // the next tile stages at most kCols / kGroup groups
           flush_pending(ps, pp, pending, thr, p.cand, p.cand_cnt, q);
           pending = 0;
         }
@@ -547,7 +588,7 @@ int score_pass_chunks(int64_t n_pos, int64_t n_query, int n_sm) {
 }
 
 size_t score_pass_pending_bytes(int64_t n_query, int n_chunks) {
-  return (size_t)ceil_div(n_query, 128) * n_chunks * kPend * kEpiThreads * (sizeof(float4) + sizeof(int32_t));
+  return (size_t)ceil_div(n_query, 128) * n_chunks * kPend * kEpiThreads * (kGroup / 4 * sizeof(float4) + sizeof(int32_t));
 }
 
 #ifdef EVAVOS_TRACE
@@ -590,7 +631,7 @@ int launch_score_select(const float* query, int64_t query_ch_stride, const void*
     const unsigned grid = (unsigned)(p.n_mtiles * n_chunks);
     p.pend_score = reinterpret_cast<float4*>(pending);
     p.pend_pos = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(pending) +
-                                            (size_t)mt_per_launch * n_chunks * kPend * kEpiThreads * sizeof(float4));
+                                            (size_t)mt_per_launch * n_chunks * (kPend * kGroup / 4) * kEpiThreads * sizeof(float4));
     EVAVOS_CUDA_OK(cudaMemsetAsync(grid_counter, 0, sizeof(unsigned int) * (size_t)p.n_mtiles, st));
     void* args[] = {&p};
     EVAVOS_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(score_select_kernel), dim3(grid),
