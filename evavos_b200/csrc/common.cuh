@@ -25,6 +25,29 @@ int cuda_fail(cudaError_t e, const char* what);
     if (_e != cudaSuccess) return ::evavos::cuda_fail(_e, #expr); \
   } while (0)
 
+// Programmatic dependent launch: a kernel launched through launch_pdl() may be scheduled while the previous kernel
+// of the stream drains (its launch latency overlaps that kernel's tail); it must call pdl_wait() before touching
+// anything the previous kernel wrote - the wait returns once that grid has completed and its writes are visible.
+// pdl_launch_dependents() lets the NEXT kernel start being scheduled early.  Both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- order-preserving float <-> uint key ------------------------------------------------------

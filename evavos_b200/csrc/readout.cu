@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256) readout_f32_kernel(
     const float* __restrict__ val_pm_all, int64_t capacity_pos, int CVfull, const int32_t* __restrict__ idx,
     const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out_all,
     int64_t out_obj_stride, int64_t out_ch_stride) {
+  pdl_wait();  // idx / weight come from the kernel before (programmatic dependent launch)
   constexpr int CV = 128 * NV;
   __shared__ float st[CV][kQPerCta + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(256) readout_bf16_kernel(
     const __nv_bfloat16* __restrict__ val_pm, int64_t capacity_pos, const int32_t* __restrict__ idx,
     const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out,
     int64_t out_obj_stride, int64_t out_ch_stride) {
+  pdl_wait();  // idx / weight come from the kernel before (programmatic dependent launch)
   constexpr int CV = 256 * NV;
   __shared__ float st[CV][kQPerCta + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(128) readout_generic_kernel(
     const VT* __restrict__ val_pm, int64_t capacity_pos, int CV, const int32_t* __restrict__ idx,
     const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out,
     int64_t out_obj_stride, int64_t out_ch_stride) {
+  pdl_wait();  // idx / weight come from the kernel before (programmatic dependent launch)
   __shared__ int32_t s_n[EVAVOS_MAX_TOPK];
   __shared__ float s_w[EVAVOS_MAX_TOPK];
   const int64_t q = blockIdx.x;
@@ -180,14 +183,14 @@ int launch_readout(const EvavosBankShadow& b, const int32_t* idx, const float* w
   if (out_obj_stride == 0) out_obj_stride = (int64_t)b.CV * n_query;
   const dim3 grid((unsigned)ceil_div(n_query, kQPerCta), (unsigned)b.K);
   const bool row16 = (reinterpret_cast<uintptr_t>(b.val_pm) % 16) == 0;
-#define EVAVOS_RO_F32(NV, SPLIT)                                                                           \
-  readout_f32_kernel<NV><<<dim3(grid.x, grid.y, SPLIT), 256, 0, st>>>(                                     \
-      reinterpret_cast<const float*>(b.val_pm), b.capacity_pos, b.CV, idx, weight, n_query, top_k, out,    \
-      out_obj_stride, out_ch_stride)
-#define EVAVOS_RO_BF16(NV)                                                                                  \
-  readout_bf16_kernel<NV><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(b.val_pm),           \
-                                                b.capacity_pos, idx, weight, n_query, top_k, out,           \
-                                                out_obj_stride, out_ch_stride)
+#define EVAVOS_RO_F32(NV, SPLIT)                                                                              \
+  EVAVOS_CUDA_OK(launch_pdl(readout_f32_kernel<NV>, dim3(grid.x, grid.y, SPLIT), dim3(256), 0, st,            \
+                            reinterpret_cast<const float*>(b.val_pm), b.capacity_pos, b.CV, idx, weight,      \
+                            n_query, top_k, out, out_obj_stride, out_ch_stride))
+#define EVAVOS_RO_BF16(NV)                                                                                    \
+  EVAVOS_CUDA_OK(launch_pdl(readout_bf16_kernel<NV>, grid, dim3(256), 0, st,                                  \
+                            reinterpret_cast<const __nv_bfloat16*>(b.val_pm), b.capacity_pos, idx, weight,    \
+                            n_query, top_k, out, out_obj_stride, out_ch_stride))
   if (b.val_dtype == EVAVOS_F32 && row16 && b.CV % 128 == 0 && b.CV <= 512) {
     // Splitting a row's channels over two CTAs (more resident warps) was measured SLOWER on B200 (55 vs 42 us at
     // cfg2: twice the L2 requests at half the size), so one warp keeps a whole value row.

@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(256) brute_select_kernel(
     const float* __restrict__ key_pm, const float* __restrict__ query, int64_t query_ch_stride, int CK,
     int64_t n_pos, int64_t n_query, int top_k, int only_overflow, int32_t* __restrict__ cand,
     int32_t* __restrict__ cand_cnt) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ __align__(16) float qs[kBruteQ][64];
   __shared__ float qq[kBruteQ];
   __shared__ int qid[kBruteQ];
@@ -190,6 +192,8 @@ __global__ void __launch_bounds__(128) finalize_kernel(
     float* __restrict__ out_score) {
   __shared__ FinalizeSmem sm;
   const int64_t q = blockIdx.x;
+  pdl_wait();
+  pdl_launch_dependents();
   if (only_flag != nullptr && only_flag[q] == 0) return;
   finalize_query(sm, threadIdx.x, q, key_pm, query, query_ch_stride, CK, top_k, cand, cand_cnt[q], out_idx,
                  out_weight, out_score, [] { __syncthreads(); });
@@ -204,18 +208,16 @@ int launch_brute_select(const float* key_pm, const float* query, int64_t query_c
   const int64_t cap = (int64_t)n_sm * 8;  // 8 resident 256-thread CTAs per SM
   if (only_overflow && grid > cap) grid = cap;
   if (grid > 0x7fffffff) grid = 0x7fffffff;
-  brute_select_kernel<<<(unsigned)grid, 256, 0, st>>>(key_pm, query, query_ch_stride, CK, n_pos, n_query, top_k,
-                                                      only_overflow, cand, cand_cnt);
-  EVAVOS_CUDA_OK(cudaGetLastError());
+  EVAVOS_CUDA_OK(launch_pdl(brute_select_kernel, dim3((unsigned)grid), dim3(256), 0, st, key_pm, query, query_ch_stride,
+                            CK, n_pos, n_query, top_k, only_overflow, cand, cand_cnt));
   return EVAVOS_OK;
 }
 
 int launch_finalize(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_query,
                     int top_k, const int32_t* cand, const int32_t* cand_cnt, const int32_t* only_flag, int32_t* out_idx,
                     float* out_weight, float* out_score, cudaStream_t st) {
-  finalize_kernel<<<(unsigned)n_query, 128, 0, st>>>(key_pm, query, query_ch_stride, CK, n_query, top_k, cand, cand_cnt,
-                                                     only_flag, out_idx, out_weight, out_score);
-  EVAVOS_CUDA_OK(cudaGetLastError());
+  EVAVOS_CUDA_OK(launch_pdl(finalize_kernel, dim3((unsigned)n_query), dim3(128), 0, st, key_pm, query, query_ch_stride,
+                            CK, n_query, top_k, cand, cand_cnt, only_flag, out_idx, out_weight, out_score));
   return EVAVOS_OK;
 }
 
