@@ -21,6 +21,7 @@ template <int K, int VEC>
 __global__ void __launch_bounds__(256) aggregate_kernel(const float* __restrict__ prob, float* __restrict__ out,
                                                         int64_t npix, int keep_bg, float scale) {
   const int64_t nvec = npix / VEC;
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
     float p[K][VEC];
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(256) aggregate_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) aggregate_generic_kernel(const float* __restrict__ prob,
                                                                 float* __restrict__ out, int K, int64_t npix,
                                                                 int keep_bg, float scale) {
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
        i += (int64_t)gridDim.x * blockDim.x) {
     float bg = 1.0f;
@@ -101,10 +103,9 @@ int launch_k(const float* prob, float* out, int64_t npix, int keep_bg, float sca
   if (grid > 148 * 16) grid = 148 * 16;  // grid-stride; a multiple of the SM count
   if (grid < 1) grid = 1;
   if (vec)
-    aggregate_kernel<K, 4><<<(unsigned)grid, 256, 0, st>>>(prob, out, npix, keep_bg, scale);
+    EVAVOS_CUDA_OK(launch_pdl(aggregate_kernel<K, 4>, dim3((unsigned)grid), dim3(256), 0, st, prob, out, npix, keep_bg, scale));
   else
-    aggregate_kernel<K, 1><<<(unsigned)grid, 256, 0, st>>>(prob, out, npix, keep_bg, scale);
-  EVAVOS_CUDA_OK(cudaGetLastError());
+    EVAVOS_CUDA_OK(launch_pdl(aggregate_kernel<K, 1>, dim3((unsigned)grid), dim3(256), 0, st, prob, out, npix, keep_bg, scale));
   return EVAVOS_OK;
 }
 
@@ -127,8 +128,7 @@ int launch_aggregate(const float* prob, float* out, int K, int64_t npix, int kee
   }
   int64_t grid = ceil_div(npix, 256);
   if (grid > 148 * 16) grid = 148 * 16;
-  aggregate_generic_kernel<<<(unsigned)grid, 256, 0, st>>>(prob, out, K, npix, keep_bg, scale);
-  EVAVOS_CUDA_OK(cudaGetLastError());
+  EVAVOS_CUDA_OK(launch_pdl(aggregate_generic_kernel, dim3((unsigned)grid), dim3(256), 0, st, prob, out, K, npix, keep_bg, scale));
   return EVAVOS_OK;
 }
 

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(256) write_keys_kernel(
     const float* __restrict__ src, int64_t src_ch_stride, int64_t pos0, int64_t n_pos, int CK,
     float* __restrict__ dst_ref, int64_t dst_ref_ch_stride, float* __restrict__ key_pm,
     uint8_t* __restrict__ tiles, float* __restrict__ maxnorm) {
+  pdl_wait();  // the bank may still be read by the kernel before this one
   __shared__ float sm[64][kKeyBlockPos + 1];
   __shared__ float warp_max[8];
   const int tid = threadIdx.x;
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(256) write_values_kernel(
     const float* __restrict__ src, int64_t src_obj_stride, int64_t src_ch_stride, int64_t pos0, int64_t n_pos,
     int CV, float* __restrict__ dst_ref, int64_t dst_ref_obj_stride, int64_t dst_ref_ch_stride,
     OutT* __restrict__ val_pm, int64_t capacity_pos) {
+  pdl_wait();  // the bank may still be read by the kernel before this one
   __shared__ float t[32][33];
   const int o = blockIdx.z;
   const int64_t p_blk = (int64_t)blockIdx.x * 32;
@@ -166,9 +168,8 @@ int launch_write_keys(const EvavosBankShadow& b, const float* src, int64_t src_c
   if (n_pos <= 0) return EVAVOS_OK;
   const int grid = (int)ceil_div(n_pos, kKeyBlockPos);
   uint8_t* tiles = (b.CK == 64) ? reinterpret_cast<uint8_t*>(b.key_tiles) : nullptr;
-  write_keys_kernel<<<grid, 256, 0, st>>>(src, src_ch_stride, pos0, n_pos, b.CK, dst_ref, dst_ref_ch_stride,
-                                          b.key_pm, tiles, b.key_maxnorm);
-  EVAVOS_CUDA_OK(cudaGetLastError());
+  EVAVOS_CUDA_OK(launch_pdl(write_keys_kernel, dim3((unsigned)grid), dim3(256), 0, st, src, src_ch_stride, pos0, n_pos,
+                            b.CK, dst_ref, dst_ref_ch_stride, b.key_pm, tiles, b.key_maxnorm));
   return EVAVOS_OK;
 }
 
@@ -179,15 +180,14 @@ int launch_write_values(const EvavosBankShadow& b, const float* src, int64_t src
   dim3 grid((unsigned)ceil_div(n_pos, 32), (unsigned)ceil_div(b.CV, 32), (unsigned)b.K);
   dim3 block(32, 8);
   if (b.val_dtype == EVAVOS_BF16) {
-    write_values_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(
-        src, src_obj_stride, src_ch_stride, pos0, n_pos, b.CV, dst_ref, dst_ref_obj_stride, dst_ref_ch_stride,
-        reinterpret_cast<__nv_bfloat16*>(b.val_pm), b.capacity_pos);
+    EVAVOS_CUDA_OK(launch_pdl(write_values_kernel<__nv_bfloat16>, grid, block, 0, st, src, src_obj_stride, src_ch_stride,
+                              pos0, n_pos, b.CV, dst_ref, dst_ref_obj_stride, dst_ref_ch_stride,
+                              reinterpret_cast<__nv_bfloat16*>(b.val_pm), b.capacity_pos));
   } else {
-    write_values_kernel<float><<<grid, block, 0, st>>>(
-        src, src_obj_stride, src_ch_stride, pos0, n_pos, b.CV, dst_ref, dst_ref_obj_stride, dst_ref_ch_stride,
-        reinterpret_cast<float*>(b.val_pm), b.capacity_pos);
+    EVAVOS_CUDA_OK(launch_pdl(write_values_kernel<float>, grid, block, 0, st, src, src_obj_stride, src_ch_stride, pos0,
+                              n_pos, b.CV, dst_ref, dst_ref_obj_stride, dst_ref_ch_stride,
+                              reinterpret_cast<float*>(b.val_pm), b.capacity_pos));
   }
-  EVAVOS_CUDA_OK(cudaGetLastError());
   return EVAVOS_OK;
 }
 

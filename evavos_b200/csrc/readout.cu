@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) readout_f32_kernel(
     const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out_all,
     int64_t out_obj_stride, int64_t out_ch_stride) {
   pdl_wait();  // idx / weight come from the kernel before (programmatic dependent launch)
+  pdl_launch_dependents();
   constexpr int CV = 128 * NV;
   __shared__ float st[CV][kQPerCta + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(256) readout_bf16_kernel(
     const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out,
     int64_t out_obj_stride, int64_t out_ch_stride) {
   pdl_wait();  // idx / weight come from the kernel before (programmatic dependent launch)
+  pdl_launch_dependents();
   constexpr int CV = 256 * NV;
   __shared__ float st[CV][kQPerCta + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -141,6 +143,7 @@ __global__ void __launch_bounds__(128) readout_generic_kernel(
     const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out,
     int64_t out_obj_stride, int64_t out_ch_stride) {
   pdl_wait();  // idx / weight come from the kernel before (programmatic dependent launch)
+  pdl_launch_dependents();
   __shared__ int32_t s_n[EVAVOS_MAX_TOPK];
   __shared__ float s_w[EVAVOS_MAX_TOPK];
   const int64_t q = blockIdx.x;
