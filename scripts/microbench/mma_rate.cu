@@ -119,22 +119,46 @@ __global__ void __launch_bounds__(640, 1) k(int n_mma, int n_readers, int flags,
     // epilogue-like readers: stream a 128x128 fp32 accumulator that the MMAs are NOT writing (columns 384..511 when
     // n_acc*width <= 384), 32 columns per tcgen05.ld, until the issuer is done
     float acc = 0.f;
+    float alu[8] = {1.f, 2.f, 3.f, 4.f, 5.f, 6.f, 7.f, 8.f};
     long long loads = 0;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     while (done < n_issuers) {
-      uint32_t r[32];
+      uint32_t r[32], r2[32];
       const uint32_t col = 384u + 32u * (uint32_t)(((warp - 4) >> 2) & 3);
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                     "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
-                     "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
-                     "=r"(r[30]), "=r"(r[31])
-                   : "r"(tmem + lane_base + col) : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#define LDTM32(R, ADDR)                                                                                               \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
+               : "=r"(R[0]), "=r"(R[1]), "=r"(R[2]), "=r"(R[3]), "=r"(R[4]), "=r"(R[5]), "=r"(R[6]), "=r"(R[7]), "=r"(R[8]), "=r"(R[9]),       \
+                 "=r"(R[10]), "=r"(R[11]), "=r"(R[12]), "=r"(R[13]), "=r"(R[14]), "=r"(R[15]), "=r"(R[16]), "=r"(R[17]), "=r"(R[18]), "=r"(R[19]), \
+                 "=r"(R[20]), "=r"(R[21]), "=r"(R[22]), "=r"(R[23]), "=r"(R[24]), "=r"(R[25]), "=r"(R[26]), "=r"(R[27]), "=r"(R[28]), "=r"(R[29]), \
+                 "=r"(R[30]), "=r"(R[31])                                                                                                         \
+               : "r"(ADDR) : "memory")
+      if (!(flags & 128)) LDTM32(r, tmem + lane_base + col);
+      if (flags & 32) LDTM32(r2, tmem + lane_base + (col ^ 32u));
+      if (flags & (64 | 128)) {
+        // ~130 dependent-free ALU instructions per lane that do not touch the load's registers
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc = fmaxf(acc, __uint_as_float(r[j]));
+        for (int j = 0; j < 128; ++j) {
+          alu[j & 7] = fmaf(alu[j & 7], 1.0001f, 0.5f);
+          // yield experiments: every 16 instructions give the scheduler a reason to switch warps
+          if ((j & 15) == 15) {
+            if (flags & 256) alu[0] = __shfl_sync(0xffffffffu, alu[0], threadIdx.x & 31);   // dependent shuffle
+            if (flags & 512) __syncwarp();
+            if (flags & 1024) asm volatile("nanosleep.u32 0;" ::: "memory");
+          }
+        }
+      }
+      if (!(flags & 128)) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc = fmaxf(acc, __uint_as_float(r[j]));
+        if (flags & 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc = fmaxf(acc, __uint_as_float(r2[j]));
+        }
+      }
       ++loads;
     }
+    acc += alu[0] + alu[1] + alu[2] + alu[3] + alu[4] + alu[5] + alu[6] + alu[7];
     if (acc == 123.f) sink[threadIdx.x] = acc;
     if ((threadIdx.x & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long*>(cycles + 1), (unsigned long long)loads);
   }
@@ -158,7 +182,10 @@ void run(long long* d, int n_readers = 0, int flags = 0, int n_copy = 0, int n_p
   if (flags || n_copy) printf("    flags: commit-per-tile=%d sw32-5th=%d overwrite-1st=%d, %d copy lanes: %.0f B/clk of bulk copies\n", flags & 1, (flags >> 1) & 1, (flags >> 2) & 1, n_copy, (double)c2[2] * 20480 / (double)c);
   if (grid > 1 || (flags & 24)) printf("    grid %d, %d issuing threads, %s operands\n", grid, (flags & 8) ? 2 : 1, (flags & 16) ? "random" : "constant");
   if (n_poll) printf("    %d warps polling an mbarrier\n", n_poll);
-  if (n_readers) printf("    with %d reader warps: TMEM read %.0f B/clk beside the MMAs\n", n_readers, (double)c2[1] * 32 * 32 * 4 / (double)c);
+  if (n_readers) printf("    with %d reader warps: TMEM read %.0f B/clk beside the MMAs; %.0f clk per reader iteration (%s%s)\n", n_readers,
+                        (double)c2[1] * 32 * 32 * 4 * ((flags & 32) ? 2 : 1) * ((flags & 128) ? 0 : 1) / (double)c / (grid > 1 ? grid : 1),
+                        (double)c * n_readers * (grid > 1 ? grid : 1) / (double)c2[1],
+                        (flags & 128) ? "ALU only" : (flags & 32) ? "two loads in flight" : "one load", (flags & 64) ? " + 128 FMA before the wait" : "");
 }
 int main() {
   long long* d; cudaMalloc(&d, 24 + 640 * 4);
@@ -173,6 +200,13 @@ int main() {
   run<1, 3, 0>(d, 0, 0, 0, 4); run<1, 3, 0>(d, 0, 0, 0, 16); run<1, 3, 0>(d, 0, 7, 4, 16); run<1, 3, 0>(d, 8, 7, 4, 8);
   run<1, 1, 0>(d, 0, 8); run<1, 1, 0>(d, 0, 15); run<1, 1, 0>(d, 16, 15, 4);
   run<1, 3, 0>(d, 0, 0, 0, 0, 143); run<1, 3, 0>(d, 16, 7, 4, 0, 143); run<1, 1, 0>(d, 16, 15, 4, 0, 143);
+  printf("--- does a tcgen05.ld block its warp? reader iteration time: ld+wait | 2 ld+wait | ld+ALU+wait | ALU only ---\n");
+  run<1, 3, 0>(d, 16, 0); run<1, 3, 0>(d, 16, 32); run<1, 3, 0>(d, 16, 64); run<1, 3, 0>(d, 16, 128);
+  run<1, 3, 0>(d, 4, 0); run<1, 3, 0>(d, 4, 32); run<1, 3, 0>(d, 4, 64); run<1, 3, 0>(d, 4, 128);
+  printf("--- ALU-only warps (16) with a yield point every 16 instructions: none | shuffle | syncwarp | nanosleep 0 ---\n");
+  run<1, 3, 0>(d, 16, 128); run<1, 3, 0>(d, 16, 128 + 256); run<1, 3, 0>(d, 16, 128 + 512); run<1, 3, 0>(d, 16, 128 + 1024);
+  printf("--- same with two issuing threads ---\n");
+  run<1, 1, 0>(d, 16, 8 + 128); run<1, 1, 0>(d, 16, 8 + 128 + 256); run<1, 1, 0>(d, 16, 8 + 128 + 1024);
   printf("--- random operands (flag 16) ---\n");
   run<0, 3, 0>(d, 0, 16, 0, 0, 1); run<0, 3, 0>(d, 0, 16, 0, 0, 143); run<0, 1, 0>(d, 16, 16 + 15, 4, 0, 143); run<0, 1, 0>(d, 16, 15, 4, 0, 143);
   for (int r : {16}) { run<1, 1, 0>(d, r); run<1, 3, 0>(d, r); run<0, 3, 0>(d, r); }
