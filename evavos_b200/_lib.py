@@ -61,6 +61,9 @@ SIGNATURES = {
     "evavos_affinity_dense": (_c_i32, [_c_vp, _c_vp, _c_i64, _c_i32, _c_i64, _c_vp, _c_vp]),
     "evavos_aggregate_wbg": (_c_i32, [_c_vp, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_vp]),
     "evavos_argmax_unpad": (_c_i32, [_c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_vp, _c_vp, _c_i32, _c_i32, _c_i32, _c_i32, _c_vp]),
+    "evavos_attention_workspace_bytes": (ctypes.c_size_t, [_c_i32, _c_i64, _c_i64, _c_i32]),
+    "evavos_attention_readout": (_c_i32, [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_i32, _c_i32, _c_i64, _c_i64,
+                                          _c_vp, _c_i64, _c_vp, _c_i64, _c_i32, _c_vp]),
     "evavos_topk_merge": (_c_i32, [_c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_i32, _c_i32, _c_i64, _c_vp, _c_vp, _c_vp,
                                    _c_vp, _c_vp]),
     "evavos_topk_merge_gathered": (_c_i32, [_c_vp, _c_i64, _c_i32, _c_i32, _c_i32, _c_i32, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp,

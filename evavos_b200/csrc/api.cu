@@ -297,6 +297,33 @@ int evavos_argmax_unpad(const float* prob, int32_t C, int64_t T, int32_t nh, int
   return launch_argmax_unpad(prob, C, T, nh, nw, masks, out, pad_top, pad_left, h, w, (cudaStream_t)stream);
 }
 
+size_t evavos_attention_workspace_bytes(int32_t n_vec, int64_t n_mem, int64_t n_query, int32_t n_sm) {
+  if (n_vec <= 0 || n_vec > 32 || n_mem <= 0 || n_query <= 0) return 0;
+  return attention_workspace_bytes(n_vec, n_mem, n_query, n_sm > 0 ? n_sm : 148);
+}
+
+int evavos_attention_readout(const float* mem_key, int64_t mem_ch_stride, const float* query_key,
+                             int64_t query_ch_stride, const float* vec, int64_t vec_row_stride, int32_t n_vec,
+                             int32_t CK, int64_t n_mem, int64_t n_query, float* out, int64_t out_row_stride,
+                             void* workspace, int64_t workspace_bytes, int32_t n_sm, evavos_stream_t stream) {
+  if (!mem_key || !query_key || !vec || !out || n_vec <= 0 || n_mem <= 0 || n_query <= 0) {
+    set_error("attention_readout: bad arguments");
+    return EVAVOS_ERR_INVALID;
+  }
+  if (CK != 64 || n_vec > 32) {
+    set_error("attention_readout: CK=%d, n_vec=%d unsupported (CK must be 64, n_vec <= 32)", (int)CK, (int)n_vec);
+    return EVAVOS_ERR_UNSUPPORTED;
+  }
+  if (n_sm <= 0) n_sm = 148;
+  if (!workspace || workspace_bytes < (int64_t)attention_workspace_bytes(n_vec, n_mem, n_query, n_sm)) {
+    set_error("attention_readout: workspace of %lld bytes, %lld needed", (long long)workspace_bytes,
+              (long long)attention_workspace_bytes(n_vec, n_mem, n_query, n_sm));
+    return EVAVOS_ERR_WORKSPACE;
+  }
+  return launch_attention_readout(mem_key, mem_ch_stride, query_key, query_ch_stride, vec, vec_row_stride, n_vec, CK,
+                                  n_mem, n_query, out, out_row_stride, workspace, n_sm, (cudaStream_t)stream);
+}
+
 int evavos_topk_merge(const int32_t* cand_idx, const float* cand_score, int64_t n_query, int32_t n_cand,
                       int32_t top_k, int32_t shard, int32_t n_shards, int64_t pos_per_frame, int32_t* out_idx,
                       float* out_weight, float* out_score, int32_t* local_idx, evavos_stream_t stream) {

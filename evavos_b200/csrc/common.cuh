@@ -126,6 +126,11 @@ int launch_aggregate(const float* prob, float* out, int K, int64_t npix, int kee
                      cudaStream_t st);
 int launch_argmax_unpad(const float* prob, int C, int64_t T, int nh, int nw, uint8_t* masks, uint8_t* out,
                         int pad_top, int pad_left, int h, int w, cudaStream_t st);
+size_t attention_workspace_bytes(int n_vec, int64_t n_mem, int64_t n_query, int n_sm);
+int launch_attention_readout(const float* mk, int64_t mk_ch_stride, const float* qk, int64_t qk_ch_stride,
+                             const float* vec, int64_t vec_row_stride, int n_vec, int CK, int64_t n_mem,
+                             int64_t n_query, float* out, int64_t out_row_stride, void* workspace, int n_sm,
+                             cudaStream_t st);
 int launch_topk_merge(const int32_t* cand_idx, const float* cand_score, int64_t n_query, int n_cand, int top_k,
                       int shard, int n_shards, int64_t pos_per_frame, int32_t* out_idx, float* out_weight,
                       float* out_score, int32_t* local_idx, int gathered, cudaStream_t st);

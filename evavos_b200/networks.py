@@ -193,7 +193,8 @@ class Decoder(nn.Module):
 class AttentionMemory(nn.Module):
     """Full-softmax affinity of one memory frame (fusion path only, prop_net.py:117-138).
 
-    Not part of the rewritten hot path yet: evaluated with stock torch ops.
+    Kept with the reference's signature for callers of ``get_W``; ``get_attention`` itself uses the fused
+    attention read (evavos_b200.attention) and never builds this matrix on the GPU.
     """
 
     def __init__(self, k):
@@ -259,12 +260,18 @@ class PropagationNetwork(nn.Module):
         return self.attn_memory(mk16, qk16)
 
     def get_attention(self, mk16, pos_mask, neg_mask, qk16):
+        """prop_net.py:198-211.  On CUDA tensors W = get_W(mk16, qk16) is never built: one fused attention read
+        (evavos_attention_readout) produces the stride-16 positive / negative maps directly."""
         b, _, h, w = pos_mask.shape
         nh, nw = h // 16, w // 16
-        W = self.get_W(mk16, qk16)
-        pos_map = F.interpolate(pos_mask, size=(nh, nw), mode="area").view(b, 1, nh * nw) @ W
-        neg_map = F.interpolate(neg_mask, size=(nh, nw), mode="area").view(b, 1, nh * nw) @ W
-        attn = torch.cat([pos_map, neg_map], 1).reshape(b, 2, nh, nw)
+        pos = F.interpolate(pos_mask, size=(nh, nw), mode="area").view(b, 1, nh * nw)
+        neg = F.interpolate(neg_mask, size=(nh, nw), mode="area").view(b, 1, nh * nw)
+        if mk16.is_cuda:
+            from .attention import attention_readout
+            attn = attention_readout(mk16, qk16, torch.cat([pos, neg], 1).view(2 * b, nh * nw)).view(b, 2, nh, nw)
+        else:  # module definition on CPU tensors (state-dict / shape tests); not a product path
+            W = self.get_W(mk16, qk16)
+            attn = torch.cat([pos @ W, neg @ W], 1).reshape(b, 2, nh, nw)
         return F.interpolate(attn, mode="bilinear", size=(h, w), align_corners=False)
 
 

@@ -18,6 +18,9 @@
  *                           174-177) and the torch.cat growth in interact (:235-240).
  *   evavos_argmax_unpad     replaces the per-frame argmax + un-padding at the end of interact
  *                           (mivos/inference_core.py:247-257).
+ *   evavos_attention_readout replaces AttentionMemory.forward + the two vector-matrix products of
+ *                           get_attention (mivos/model/propagation/prop_net.py:117-138, 204-207) without
+ *                           materialising the (HW, HW) softmax matrix.
  *   evavos_topk_merge       the exchange step of the memory-axis sharded read
  *                           (no reference counterpart).
  *   evavos_memread_host     the same read with HOST buffers in the reference layout
@@ -171,6 +174,19 @@ int evavos_aggregate_wbg(const float* prob, float* out, int32_t K, int64_t npix,
  */
 int evavos_argmax_unpad(const float* prob, int32_t C, int64_t T, int32_t nh, int32_t nw, uint8_t* masks, uint8_t* out,
                         int32_t pad_top, int32_t pad_left, int32_t h, int32_t w, evavos_stream_t stream);
+
+/*
+ * Full-softmax attention read of ONE memory frame (the fusion path, prop_net.py:117-138 and :204-207):
+ *   out[c][q] = sum_n vec[c][n] * softmax_n((-|m_n|^2 + 2 m_n.q_q - |q_q|^2) / sqrt(CK))
+ * mem_key (CK, n_mem) and query_key (CK, n_query) fp32 with the given channel strides, unit position stride;
+ * vec (n_vec, n_mem) fp32 rows (area-interpolated positive / negative interaction masks), n_vec <= 32;
+ * out (n_vec, n_query) fp32.  CK must be 64.  workspace: evavos_attention_workspace_bytes() bytes.
+ */
+size_t evavos_attention_workspace_bytes(int32_t n_vec, int64_t n_mem, int64_t n_query, int32_t n_sm);
+int evavos_attention_readout(const float* mem_key, int64_t mem_ch_stride, const float* query_key,
+                             int64_t query_ch_stride, const float* vec, int64_t vec_row_stride, int32_t n_vec,
+                             int32_t CK, int64_t n_mem, int64_t n_query, float* out, int64_t out_row_stride,
+                             void* workspace, int64_t workspace_bytes, int32_t n_sm, evavos_stream_t stream);
 
 /*
  * Merge step of the memory-axis sharded read.  cand_idx/cand_score: (n_query, n_cand)

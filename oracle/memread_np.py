@@ -221,3 +221,16 @@ def sharded_memory_read(mk, qk, mv, k, owners):
         mask = np.isin(gi, own)
         total += readout(gi, np.where(mask, w, 0.0), mv)
     return TopK(gi, gs, w, np.zeros(hw)), total
+
+
+def attention_readout(mk: np.ndarray, qk: np.ndarray, vec: np.ndarray) -> np.ndarray:
+    """vec @ softmax_n(S), fp64: AttentionMemory.forward (prop_net.py:123-138) followed by the
+    vector-matrix products of get_attention (:204-205).
+
+    mk (CK, M), qk (CK, Q), vec (C, M) -> (C, Q).
+    """
+    s = affinity_scores(mk, qk)                       # (M, Q) fp64, (-a + b - c) / sqrt(CK)
+    s = s - s.max(axis=0, keepdims=True)
+    w = np.exp(s)
+    w /= w.sum(axis=0, keepdims=True)
+    return vec.astype(np.float64) @ w

@@ -14,6 +14,7 @@ from __future__ import annotations
 import math
 
 import torch
+import torch.nn.functional as F
 
 
 def dense_topk_affinity(mem_key: torch.Tensor, query_key: torch.Tensor, top_k: int = 50) -> torch.Tensor:
@@ -61,3 +62,35 @@ def aggregate_wbg(prob: torch.Tensor, keep_bg: bool = False, hard: bool = False)
         logit *= 1000
     sm = torch.softmax(logit, dim=0)
     return sm if keep_bg else sm[1:]
+
+
+def attention_weights(mem_key: torch.Tensor, query_key: torch.Tensor) -> torch.Tensor:
+    """AttentionMemory.forward, prop_net.py:123-138: full softmax over the ONE memory frame.
+
+    mem_key (B,CK,1,H,W) (or any (B,CK,...) that flattens to THW), query_key (B,CK,H,W) -> W (B,THW,HW).
+    """
+    ck = mem_key.shape[1]
+    mk = mem_key.flatten(start_dim=2)
+    qk = query_key.flatten(start_dim=2)
+    a = mk.pow(2).sum(1).unsqueeze(2)
+    b = 2 * (mk.transpose(1, 2) @ qk)
+    c = qk.pow(2).sum(1).unsqueeze(1)
+    affinity = (-a + b - c) / math.sqrt(ck)
+    return F.softmax(affinity, dim=1)
+
+
+def attention_lowres(mem_key, pos_mask, neg_mask, query_key) -> torch.Tensor:
+    """The stride-16 part of get_attention, prop_net.py:198-208: (b,2,nh,nw) positive / negative attention."""
+    b, _, h, w = pos_mask.shape
+    nh, nw = h // 16, w // 16
+    W = attention_weights(mem_key, query_key)
+    pos_map = F.interpolate(pos_mask, size=(nh, nw), mode="area").view(b, 1, nh * nw) @ W
+    neg_map = F.interpolate(neg_mask, size=(nh, nw), mode="area").view(b, 1, nh * nw) @ W
+    return torch.cat([pos_map, neg_map], 1).reshape(b, 2, nh, nw)
+
+
+def get_attention(mem_key, pos_mask, neg_mask, query_key) -> torch.Tensor:
+    """PropagationNetwork.get_attention, prop_net.py:198-211: (b,2,h,w)."""
+    h, w = pos_mask.shape[-2:]
+    return F.interpolate(attention_lowres(mem_key, pos_mask, neg_mask, query_key), mode="bilinear", size=(h, w),
+                         align_corners=False)

@@ -100,3 +100,19 @@ def test_oracle_sharded_equals_single():
         tk2, ro2 = onp.sharded_memory_read(mkf, qkf, mvf, 50, owners)
         assert (tk2.idx == tk.idx).all()
         assert np.abs(ro2 - ro).max() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["b2", "b4_peaky", "b1_flat"])
+def test_oracle_attention(name):
+    """Fusion-path attention (prop_net.py:117-138, 198-211): torch port bit-exact, fp64 oracle within fp32 rounding."""
+    g = load("attention.npz")
+    mk, qk = torch.from_numpy(g[f"{name}_mk"]), torch.from_numpy(g[f"{name}_qk"])
+    pos, neg = torch.from_numpy(g[f"{name}_pos"]), torch.from_numpy(g[f"{name}_neg"])
+    assert torch.equal(port.get_attention(mk, pos, neg, qk), torch.from_numpy(g[f"{name}_attn"]))
+    low = port.attention_lowres(mk, pos, neg, qk)
+    assert torch.equal(low, torch.from_numpy(g[f"{name}_lowres"]))
+    b, _, nh, nw = low.shape
+    vec = torch.stack([torch.nn.functional.interpolate(pos, size=(nh, nw), mode="area").view(b, -1),
+                       torch.nn.functional.interpolate(neg, size=(nh, nw), mode="area").view(b, -1)], 1)
+    o64 = onp.attention_readout(mk.reshape(64, -1).numpy(), qk.reshape(64, -1).numpy(), vec.reshape(2 * b, -1).numpy())
+    assert np.abs(o64.reshape(b, 2, nh, nw) - low.numpy()).max() < 2e-6
