@@ -41,14 +41,33 @@ __device__ __forceinline__ void dot_row(const float4* __restrict__ krow, const f
   }
 }
 
+// The same arithmetic on a row that already sits in shared memory (CK == 64): identical FMA order, plain loads.
+__device__ __forceinline__ void dot_row_smem64(const float4* krow, const float* q, float& kk, float& kq) {
+  kk = 0.f;
+  kq = 0.f;
+#pragma unroll
+  for (int c4 = 0; c4 < 16; ++c4) {
+    const float4 kv = krow[c4];
+    const float4 qv = *reinterpret_cast<const float4*>(q + 4 * c4);
+    kk = fmaf(kv.x, kv.x, kk); kq = fmaf(kv.x, qv.x, kq);
+    kk = fmaf(kv.y, kv.y, kk); kq = fmaf(kv.y, qv.y, kq);
+    kk = fmaf(kv.z, kv.z, kk); kq = fmaf(kv.z, qv.z, kq);
+    kk = fmaf(kv.w, kv.w, kk); kq = fmaf(kv.w, qv.w, kq);
+  }
+}
+
 __device__ __forceinline__ float sumsq(const float* __restrict__ q, int CK) {
   float s = 0.f;
   for (int c = 0; c < CK; ++c) s = fmaf(q[c], q[c], s);
   return s;
 }
 
+constexpr int kRowChunk = 48;    // candidate key rows staged per round (finalize_query)
+constexpr int kRowStride = 68;   // floats: 16-byte aligned rows, conflict-free LDS.128 when every lane owns a row
+
 struct FinalizeSmem {
   float qs[64];
+  float rows[kRowChunk][kRowStride];
   unsigned long long keys[kCandCap];
   unsigned long long sel[EVAVOS_MAX_TOPK];
   float warp_sum[4];
@@ -66,29 +85,52 @@ __device__ __forceinline__ void finalize_query(FinalizeSmem& sm, int tid, int64_
                                                float* __restrict__ out_score, Sync sync) {
   const int lane = tid & 31, warp = tid >> 5;
   const int cnt = min(cnt_raw, kCandCap);
-  int32_t my_n[kCandCap / 128];
-#pragma unroll
-  for (int t = 0; t < kCandCap / 128; ++t) {
-    const int ci = tid + 128 * t;
-    my_n[t] = ci < cnt ? __ldcg(cand + q * kCandCap + ci) : -1;
-  }
   if (tid < 64) sm.qs[tid] = (tid < CK) ? __ldg(query + (int64_t)tid * query_ch_stride + q) : 0.f;
   sync();
-  const float qq = EVAVOS_FIN_SKIP(4) ? 1.f : sumsq(sm.qs, CK);
   const float inv_sqrt_ck = 1.0f / sqrtf((float)CK);
+  if (CK == 64) {
+    // |q|^2 once per warp (two channels per lane) instead of a 64-step chain in every thread
+    float qq = fmaf(sm.qs[lane], sm.qs[lane], sm.qs[lane + 32] * sm.qs[lane + 32]);
 #pragma unroll
-  for (int t = 0; t < kCandCap / 128; ++t) {
-    const int ci = tid + 128 * t;
-    unsigned long long key = 0ull;
-    if (my_n[t] >= 0) {
-      float kk = (float)my_n[t], kq = 1.f;
-      if (!EVAVOS_FIN_SKIP(1)) dot_row(reinterpret_cast<const float4*>(key_pm + (int64_t)my_n[t] * CK), sm.qs, CK, kk, kq);
-      const float s = affinity_from_parts(kk, kq, qq, inv_sqrt_ck);
-      key = ((unsigned long long)float_to_ordered(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)my_n[t]);
+    for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    // Candidate rows go through shared memory: half a warp fetches one 256-byte row (two full lines per row and
+    // instruction instead of 32 partial ones when every thread walks its own row), then thread t rescoring row t
+    // reads it back with the FMA order of dot_row.
+    for (int base = 0; base < cnt; base += kRowChunk) {
+      const int nrows = min(kRowChunk, cnt - base);
+      if (!EVAVOS_FIN_SKIP(1)) {
+        for (int r = tid >> 4; r < nrows; r += 8) {
+          const int32_t n = __ldcg(cand + q * kCandCap + base + r);
+          const float4 v = __ldg(reinterpret_cast<const float4*>(key_pm + (int64_t)n * 64) + (tid & 15));
+          *reinterpret_cast<float4*>(&sm.rows[r][4 * (tid & 15)]) = v;
+        }
+      }
+      sync();
+      if (tid < nrows) {
+        const int32_t n = __ldcg(cand + q * kCandCap + base + tid);
+        float kk, kq;
+        dot_row_smem64(reinterpret_cast<const float4*>(sm.rows[tid]), sm.qs, kk, kq);
+        const float s = affinity_from_parts(kk, kq, qq, inv_sqrt_ck);
+        sm.keys[base + tid] =
+            ((unsigned long long)float_to_ordered(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
+      }
+      sync();
     }
-    sm.keys[ci] = key;
+  } else {
+    const float qq = sumsq(sm.qs, CK);
+#pragma unroll
+    for (int t = 0; t < kCandCap / 128; ++t) {
+      const int ci = tid + 128 * t;
+      if (ci < cnt) {
+        const int32_t n = __ldcg(cand + q * kCandCap + ci);
+        float kk, kq;
+        dot_row(reinterpret_cast<const float4*>(key_pm + (int64_t)n * CK), sm.qs, CK, kk, kq);
+        const float s = affinity_from_parts(kk, kq, qq, inv_sqrt_ck);
+        sm.keys[ci] = ((unsigned long long)float_to_ordered(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
+      }
+    }
+    sync();
   }
-  sync();
   const int take = min(top_k, cnt);
 #pragma unroll
   for (int t = 0; t < kCandCap / 128; ++t) {

@@ -182,9 +182,10 @@ __global__ void __launch_bounds__(256) brute_select_kernel(
   }
 }
 
-// One 128-thread CTA per query (see finalize_query).  Measured on B200: ~20 us for 1620 queries whether a CTA takes
-// one query or four, and whether a candidate row is read by one thread or four - neither launch rate nor the
-// row loads bound it; a round-2 item.  only_flag != nullptr: only queries flagged there.
+// One 128-thread CTA per query (see finalize_query).  Measured on B200 at cfg2: 22 us with every thread walking its
+// own key row in global memory (L1/TEX 70 % busy: 32 partial lines per load instruction), 19.7 us with the rows
+// staged through shared memory by half-warps; one or four queries per CTA makes no difference.
+// only_flag != nullptr: only queries flagged there.
 __global__ void __launch_bounds__(128) finalize_kernel(
     const float* __restrict__ key_pm, const float* __restrict__ query, int64_t query_ch_stride, int CK,
     int64_t n_query, int top_k, const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt,

@@ -191,15 +191,15 @@ class InferenceCore:
 
     def fuse_one_frame(self, tc, tr, ti, prev_mask, curr_mask, mk16, qk16):
         assert (tc < ti < tr or tr < ti < tc)
-        prob = torch.zeros((self.k, 1, self.nh, self.nw), dtype=torch.float32, device=self.device)
         nc = abs(tc - ti) / abs(tc - tr)
         nr = abs(tr - ti) / abs(tc - tr)
         dist = torch.tensor([[nc, nr]], dtype=torch.float32, device=self.device)
         attn_map = self.prop_net.get_attention(mk16, self.pos_mask_diff, self.neg_mask_diff, qk16)
-        for k in range(1, self.k + 1):
-            w = torch.sigmoid(self.fuse_net(self.get_image_buffered(ti), prev_mask[k:k + 1].to(self.device),
-                                            curr_mask[k:k + 1].to(self.device), attn_map[k:k + 1], dist))
-            prob[k - 1] = w
+        # all objects in one batched pass of the fusion net (the reference loops k = 1..K with batch 1, :200-204)
+        k = self.k
+        prob = torch.sigmoid(self.fuse_net(self.get_image_buffered(ti).expand(k, -1, -1, -1),
+                                           prev_mask[1:k + 1].to(self.device), curr_mask[1:k + 1].to(self.device),
+                                           attn_map[1:k + 1], dist.expand(k, -1)))
         return aggregate_wbg(prob, keep_bg=True)
 
     # ------------------------------------------------------------------ interaction (inference_core.py:209-259)
