@@ -49,7 +49,7 @@ WORKLOADS = {
 TOP_K = 50
 N_BANKS = 4
 FRAMES_PER_EXCHANGE = 5   # query frames between two memory appends (mem_freq) read in one sharded exchange
-KERNELS_PER_STEP = 7  # pass 1, threshold, pass 2, exact-select (overflow), finalize, readout, aggregate
+KERNELS_PER_STEP = 5  # fused score filter, exact fallback (overflow), finalize, readout, aggregate (+ one memset node)
 
 
 def synth(seed, ck, cv, t, h, w, k):
@@ -295,7 +295,7 @@ def run_cfg5(args, cfg, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": args.workload + ": " + desc, "top_k": TOP_K, "memory_positions": n_pos, "queries_per_frame": hw,
                    "objects": k, "l2": f"{n_banks} rotating banks of {2 * k * cv * n_pos / 1e9:.1f} GB"},
-        "gpu_launches": 5 * args.steps,
+        "gpu_launches": KERNELS_PER_STEP * args.steps,
         "stages_us": {"filter": acc[0] * 1e3, "exact_fallback": acc[1] * 1e3, "finalize": acc[2] * 1e3, "readout": acc[3] * 1e3},
         "roofline": {"bound": "balanced (SURVEY 8d: 308 us tensor vs 333 us HBM)", "achieved": None, "peak": None,
                      "unit": "fraction of max(F_alg / P_tc, B_alg / BW_hbm)", "frac": t_roof / (elapsed_ms / args.steps * 1e-3),
