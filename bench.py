@@ -516,7 +516,8 @@ def run_ours(args, cfg, rank, world, local_rank):
                 "d2h_bytes_per_step": int(s_d2h), "steps": s_steps,
                 "note": "public API, pinned host buffers, synchronised every step: H2D query key + decoder probabilities + "
                         "(every 5th step) one new memory frame appended in place; D2H readout + aggregated probabilities; "
-                        "the bank itself is engine state, as in the reference"},
+                        "the bank itself is engine state, as in the reference.  (A two-frames-in-flight variant with the "
+                        "copies on their own streams was measured slower on this platform: 484 vs 1047 qf/s.)"},
         "e2e_full_upload": {"value": world * e2e_steps / e2e_s, "unit": "query-frames/s", "h2d_bytes_per_step": int(h2d_b),
                             "d2h_bytes_per_step": int(d2h_b), "steps": e2e_steps,
                             "note": "evavos_memread_host: stateless, the whole bank + query H2D, shadow build, read, D2H, every step"},
