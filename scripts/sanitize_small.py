@@ -28,5 +28,7 @@ idx, sc = ops.local_topk(bank, qk, 50)
 packed = torch.stack([idx, sc.view(torch.int32)], -1).unsqueeze(0).contiguous()
 gi, w, loc = ops.merge_gathered(packed, 50, 0, 1, H * W)
 part = ops.readout(bank, loc, w)
+att = ev.attention_readout(mk[:, :, 1:2], qk, torch.rand(6, H * W, generator=g).to(dev))      # fusion-path attention read
+masks, unp = ev.argmax_unpad(torch.rand(3, 4, 1, 32, 48, device=dev), (3, 5, 2, 6), 24, 40)
 torch.cuda.synchronize()
 print("sanitize run ok", float(out.abs().mean()), float(part.abs().mean()))
