@@ -61,6 +61,10 @@ constexpr int kCols = 32;       // accumulator columns per epilogue thread
 #endif
 constexpr int kGroup = EVAVOS_GROUP;
 constexpr int kPend = 8 + kCols / kGroup;  // staged hit groups per epilogue thread (flushed when more than 8 wait)
+#ifndef EVAVOS_SPLIT
+#define EVAVOS_SPLIT 1
+#endif
+constexpr bool kSplit = EVAVOS_SPLIT != 0;   // epilogue warp groups on alternate tiles (see the epilogue)
 constexpr int kBarBytes = 256;
 constexpr int kSmemBytes = kTileBytes * kStages + kBarBytes + 1024;
 
@@ -105,17 +109,7 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, one CTA.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Same with A taken from TMEM (128 lanes x 8 columns of packed bf16 pairs per K = 16 step).
+// D[tmem] (+)= A[tmem] * B[smem]^T, bf16 x bf16 -> fp32, one CTA: A from TMEM (128 lanes x 8 columns of packed bf16 pairs per K = 16 step).
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
@@ -368,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
     }
     for (int a = 0; a < kAccStages; ++a) {
       mbar_init(bar_acc_full + 8 * a, 1);
-      mbar_init(bar_acc_empty + 8 * a, kEpiThreads / 32);
+      mbar_init(bar_acc_empty + 8 * a, kSplit ? kEpiThreads / 64 : kEpiThreads / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -440,7 +434,12 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
     //  other's MMAs: 830 -> 600 clk per tile.  Three threads, or one thread interleaving two tiles, were slower.
     //  Each commit tracks the MMAs of its own thread, which is exactly one tile.)
     const uint32_t a_tmem = tmem_base + kQueryCol;
-    for (int i = warp - 1; i < n_iter; i += 2) {
+    // kSplit: ONE issuer, every iteration in order.  The epilogue groups then see an accumulator stage only at every
+    // other use, and an mbarrier parity wait is only sound for a waiter that cannot fall two phases behind: with
+    // two issuers tile i + 1 may complete before tile i, a group runs ahead onto a stage whose previous phase it
+    // never observed, takes the stale parity for "ready" and the pipeline deadlocks (seen on B200).  In-order
+    // commits from a single thread rule that out.
+    for (int i = kSplit ? (warp == 1 ? 0 : n_iter) : warp - 1; i < n_iter; i += kSplit ? 1 : 2) {
       const int s = i % kStages, a = i % kAccStages;
       mbar_wait(bar_full + 8 * s, (uint32_t)((i / kStages) & 1));
       mbar_wait(bar_acc_empty + 8 * a, (uint32_t)(((i / kAccStages) & 1) ^ 1));
@@ -463,43 +462,58 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> running class max (sweep 1) / staged hit groups (sweep 2) =====
+    // kSplit: the 16 warps form two groups of 8 that serve alternate tiles (even / odd tile index), each warp 64
+    // accumulator columns as two 32-column loads, so that one group's math overlaps the other group's loads and
+    // the MMAs of the next tile.  Otherwise all 16 warps visit every tile in lock-step, 32 columns each.
     const int ew = warp - 4;
     const int quarter = ew & 3;           // TMEM lane quarter this warp may access
-    const int col0 = (ew >> 2) * kCols;   // accumulator columns of this warpgroup
+    const int grp = kSplit ? (ew >> 3) : 0;
+    const int colbase = kSplit ? ((ew >> 2) & 1) * 64 : (ew >> 2) * kCols;
+    constexpr int kBlocks = kSplit ? 2 : 1;   // 32-column loads per visited tile
     const int row = quarter * 32 + lane;
     const int et = threadIdx.x - 128;
     const int64_t q = (int64_t)m_tile * 128 + row;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    // first sweep-1 iteration of this warp and its stride
+    const int i_first = kSplit ? ((((t0 & 1) == grp) ? 0 : 1)) : 0;
+    constexpr int i_step = kSplit ? 2 : 1;
 
-    auto load_tile = [&](int i, float* v) {
+    // visit(i, math): wait for accumulator tile i, read this warp's columns block by block (the stage goes back to
+    // the MMA warps as soon as the last block is in registers) and call math(block, values, first position).
+    auto visit = [&](int i, auto&& math) {
       const int a = i % kAccStages;
       mbar_wait(bar_acc_full + 8 * a, (uint32_t)((i / kAccStages) & 1));
       tc_fence_after();
       if (threadIdx.x == 128) EVAVOS_TR(3, i);
-      if constexpr (!(EVAVOS_EXP & 1)) {
-        tmem_ld32(lane_addr + (uint32_t)(a * 128 + col0), v);
-        tmem_ld_wait();
-      } else {
-        for (int j = 0; j < kCols; ++j) v[j] = kEmptyNh;
+#pragma unroll
+      for (int blk = 0; blk < kBlocks; ++blk) {
+        float v[kCols];
+        if constexpr (!(EVAVOS_EXP & 1)) {
+          tmem_ld32(lane_addr + (uint32_t)(a * 128 + colbase + blk * kCols), v);
+          tmem_ld_wait();
+        } else {
+          for (int j = 0; j < kCols; ++j) v[j] = kEmptyNh;
+        }
+        if (blk == kBlocks - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * a);  // registers hold the tile: release the TMEM stage
+          if (threadIdx.x == 128) EVAVOS_TR(4, i);
+        }
+        math(blk, v, (int64_t)tile_of(i) * kTilePos + colbase + blk * kCols);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * a);  // registers hold the tile: release the TMEM stage
-      if (threadIdx.x == 128) EVAVOS_TR(4, i);
+      if (threadIdx.x == 128) EVAVOS_TR(5, i);
     };
 
     // ---- sweep 1: class maxima ----
     {
+      // Column classes per thread: 16 x (columns j and j + 16 of a 32-column block), one set per block (kSplit: of
+      // the tiles of this group's parity) or per tile parity (lock-step) - 128 per query and chunk either way.  Any
+      // partition of the positions into classes gives a valid bound; this one costs one FMNMX3 per two scores.
       float cmax[kCols];
 #pragma unroll
       for (int j = 0; j < kCols; ++j) cmax[j] = kEmptyNh;
-      // Column classes: (tile parity, column mod 16) per thread, i.e. 2 x 4 x 16 = 128 per query
-      // and chunk - any partition of the positions into classes gives a valid bound, this one costs one FMNMX3
-      // per two scores.  cmax[0..15] collects the even tiles, cmax[16..31] the odd ones.
-      auto tile_max = [&](int i, float* cm) {
-        float v[kCols];
-        load_tile(i, v);
-        const int64_t n0 = (int64_t)tile_of(i) * kTilePos + col0;
+      auto class_max = [&](float* cm, const float* v, int64_t n0) {
         int pending = 0;
         if constexpr ((EVAVOS_EXP & 2) != 0) {
         } else if (n0 + kCols > p.n_pos) {
@@ -508,15 +522,19 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
         } else {
           consume_tile<1, false>(v, cm, 0.f, (int32_t)n0, kCols, nullptr, nullptr, pending);
         }
-        if (threadIdx.x == 128) EVAVOS_TR(5, i);
       };
-      int i = 0;
-      if (t0 & 1) tile_max(i++, cmax + kCols / 2);  // parity of the tile's index in the bank, not in the chunk
-      for (; i < n_tiles; i += 2) {
-        tile_max(i, cmax);
-        if (i + 1 < n_tiles) tile_max(i + 1, cmax + kCols / 2);
+      if constexpr (kSplit) {
+        for (int i = i_first; i < n_tiles; i += i_step)
+          visit(i, [&](int blk, const float* v, int64_t n0) { class_max(blk == 0 ? cmax : cmax + kCols / 2, v, n0); });
+      } else {
+        int i = 0;   // parity of the tile's index in the bank, not in the chunk
+        if (t0 & 1) visit(i++, [&](int, const float* v, int64_t n0) { class_max(cmax + kCols / 2, v, n0); });
+        for (; i < n_tiles; i += 2) {
+          visit(i, [&](int, const float* v, int64_t n0) { class_max(cmax, v, n0); });
+          if (i + 1 < n_tiles) visit(i + 1, [&](int, const float* v, int64_t n0) { class_max(cmax + kCols / 2, v, n0); });
+        }
       }
-      float4* dst = reinterpret_cast<float4*>(p.class_max + ((int64_t)chunk * p.nq_pad + q) * 128 + col0);
+      float4* dst = reinterpret_cast<float4*>(p.class_max + ((int64_t)chunk * p.nq_pad + q) * 128 + (ew >> 2) * kCols);
 #pragma unroll
       for (int j4 = 0; j4 < kCols / 4; ++j4)
         dst[j4] = make_float4(cmax[j4 * 4], cmax[j4 * 4 + 1], cmax[j4 * 4 + 2], cmax[j4 * 4 + 3]);
@@ -545,22 +563,20 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
       int32_t* pp = p.pend_pos + (int64_t)blockIdx.x * kPend * kEpiThreads + et;
       int pending = 0;
       float unused[1];
-      for (int i = n_tiles; i < n_iter; ++i) {
-        float v[kCols];
-        load_tile(i, v);
-        const int64_t n0 = (int64_t)tile_of(i) * kTilePos + col0;
-        if constexpr ((EVAVOS_EXP & 2) != 0) {
-        } else if (n0 + kCols > p.n_pos) {
-          const int valid = (int)max((int64_t)0, p.n_pos - n0);
-          consume_tile<2, true>(v, unused, thr, (int32_t)n0, valid, ps, pp, pending);
-        } else {
-          consume_tile<2, false>(v, unused, thr, (int32_t)n0, kCols, ps, pp, pending);
-        }
-        if (pending > kPend - kCols / kGroup) {  // the next tile stages at most kCols / kGroup groups
-          flush_pending(ps, pp, pending, thr, p.cand, p.cand_cnt, q);
-          pending = 0;
-        }
-        if (threadIdx.x == 128) EVAVOS_TR(5, i);
+      for (int i = n_tiles + i_first; i < n_iter; i += i_step) {
+        visit(i, [&](int, const float* v, int64_t n0) {
+          if constexpr ((EVAVOS_EXP & 2) != 0) {
+          } else if (n0 + kCols > p.n_pos) {
+            const int valid = (int)max((int64_t)0, p.n_pos - n0);
+            consume_tile<2, true>(v, unused, thr, (int32_t)n0, valid, ps, pp, pending);
+          } else {
+            consume_tile<2, false>(v, unused, thr, (int32_t)n0, kCols, ps, pp, pending);
+          }
+          if (pending > kPend - kCols / kGroup) {  // the next block stages at most kCols / kGroup groups
+            flush_pending(ps, pp, pending, thr, p.cand, p.cand_cnt, q);
+            pending = 0;
+          }
+        });
       }
       if (pending > 0) flush_pending(ps, pp, pending, thr, p.cand, p.cand_cnt, q);
       if (threadIdx.x == 128) EVAVOS_TR(0, 58);

@@ -65,6 +65,16 @@ __device__ __forceinline__ float sumsq(const float* __restrict__ q, int CK) {
 constexpr int kRowChunk = 48;    // candidate key rows staged per round (finalize_query)
 constexpr int kRowStride = 68;   // floats: 16-byte aligned rows, conflict-free LDS.128 when every lane owns a row
 
+// |q|^2 of a 64-channel query held in shared memory, by one converged warp: two channels per lane, butterfly sum.
+// Every kernel that scores against an exact key uses THIS order for CK == 64 (a different rounding of |q|^2 would
+// let two paths break a near-tie at the top-k boundary differently).
+__device__ __forceinline__ float sumsq64_warp(const float* q, int lane) {
+  float s = fmaf(q[lane], q[lane], q[lane + 32] * q[lane + 32]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
 struct FinalizeSmem {
   float qs[64];
   float rows[kRowChunk][kRowStride];
@@ -90,9 +100,7 @@ __device__ __forceinline__ void finalize_query(FinalizeSmem& sm, int tid, int64_
   const float inv_sqrt_ck = 1.0f / sqrtf((float)CK);
   if (CK == 64) {
     // |q|^2 once per warp (two channels per lane) instead of a 64-step chain in every thread
-    float qq = fmaf(sm.qs[lane], sm.qs[lane], sm.qs[lane + 32] * sm.qs[lane + 32]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    const float qq = sumsq64_warp(sm.qs, lane);
     // Candidate rows go through shared memory: half a warp fetches one 256-byte row (two full lines per row and
     // instruction instead of 32 partial ones when every thread walks its own row), then thread t rescoring row t
     // reads it back with the FMA order of dot_row.

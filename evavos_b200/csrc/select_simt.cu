@@ -96,7 +96,14 @@ __global__ void __launch_bounds__(256) brute_select_kernel(
       qs[j][c] = (q >= 0 && c < CK) ? query[(int64_t)c * query_ch_stride + q] : 0.f;
     }
     __syncthreads();
-    if (tid < kBruteQ) qq[tid] = sumsq(qs[tid], CK);
+    if (CK == 64) {   // the same |q|^2 arithmetic as finalize_query
+      if ((tid >> 5) < kBruteQ) {
+        const float v = sumsq64_warp(qs[tid >> 5], tid & 31);
+        if ((tid & 31) == 0) qq[tid >> 5] = v;
+      }
+    } else if (tid < kBruteQ) {
+      qq[tid] = sumsq(qs[tid], CK);
+    }
     __syncthreads();
 
     // ---- 4 radix rounds, most significant byte first --------------------------------------
