@@ -7,7 +7,7 @@ if it has not been built (no CPU fallback).
 """
 from . import _lib
 from ._lib import EvavosError
-from .aggregate import aggregate_wbg, argmax_unpad
+from .aggregate import aggregate_wbg, argmax_unpad, get_segmentations
 from .attention import attention_readout
 from .memory_bank import MemoryBank
 from .memory_reader import EvalMemoryReader, TopKAffinity, memory_read
@@ -15,5 +15,5 @@ from .networks import FusionNet, PropagationNetwork
 from .inference_core import InferenceCore
 from .tensor_util import pad_divide_by
 
-__all__ = ["EvavosError", "aggregate_wbg", "argmax_unpad", "attention_readout", "MemoryBank", "EvalMemoryReader", "TopKAffinity", "memory_read",
+__all__ = ["EvavosError", "aggregate_wbg", "argmax_unpad", "get_segmentations", "attention_readout", "MemoryBank", "EvalMemoryReader", "TopKAffinity", "memory_read",
            "PropagationNetwork", "FusionNet", "InferenceCore", "pad_divide_by", "_lib"]

@@ -44,3 +44,15 @@ def argmax_unpad(prob: torch.Tensor, pad, h: int, w: int):
         _lib.check(lib.evavos_argmax_unpad(p.data_ptr(), c, t, nh, nw, masks.data_ptr(), out.data_ptr(), int(pad[2]),
                                            int(pad[0]), int(h), int(w), _lib.current_stream_ptr(prob.device)))
     return masks, out
+
+
+def get_segmentations(processor, rgb=None, device="cuda"):
+    """interactions/eval.py:8-24: un-padded per-frame argmax of ``processor.prob`` times 255, uint8 (T,h,w) numpy.
+
+    One fused argmax + un-padding launch over all frames instead of T argmax launches into a float buffer.  With
+    more than one object the reference's ``argmax * 255`` leaves the uint8 range (its float -> uint8 cast wraps);
+    the same wrap is kept here.  ``rgb`` is only used for its spatial size, as in the reference.
+    """
+    h, w = (processor.h, processor.w) if rgb is None else tuple(rgb.shape[-2:])
+    _, unpadded = argmax_unpad(processor.prob.to(device), processor.pad, h, w)
+    return (unpadded * 255).cpu().numpy()   # uint8 arithmetic: (k * 255) mod 256

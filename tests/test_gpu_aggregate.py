@@ -60,3 +60,25 @@ def test_argmax_unpad_matches_torch(shape, hw):
     assert torch.equal(masks.cpu(), ref)
     assert torch.equal(out.cpu(), ref[:, 0, lh:lh + h, lw:lw + w])
     assert out.is_contiguous() and out.dtype == torch.uint8
+
+
+@pytest.mark.parametrize("k", [1, 2])
+def test_get_segmentations_matches_reference_formula(k):
+    """interactions/eval.py:8-24 restated with torch ops on the CPU (the module itself needs skimage/torchmetrics)."""
+    import types
+    import evavos_b200 as ev
+    g = torch.Generator().manual_seed(9 + k)
+    t, h, w = 5, 100, 140
+    nh, nw = 112, 144
+    pad = ((nw - w) // 2, nw - w - (nw - w) // 2, (nh - h) // 2, nh - h - (nh - h) // 2)   # (lw, uw, lh, uh)
+    prob = torch.rand(k + 1, t, 1, nh, nw, generator=g)
+    proc = types.SimpleNamespace(prob=prob.cuda(), pad=pad, t=t, h=h, w=w)
+    got = ev.get_segmentations(proc, torch.zeros(3, h, w))
+    want = np.zeros((t, h, w), dtype=np.uint8)
+    for ti in range(t):
+        p = prob[:, ti]
+        p = p[:, :, pad[2]:-pad[3], :]
+        p = p[:, :, :, pad[0]:-pad[1]]
+        want[ti] = ((torch.argmax(p, dim=0)[0].numpy().astype(np.int64) * 255) % 256).astype(np.uint8)
+    assert got.dtype == np.uint8 and got.shape == (t, h, w)
+    assert (got == want).all()
