@@ -12,6 +12,8 @@ that call ``processor.interact(mask, frame)`` run unchanged.  What differs under
 * query frames between two memory appends read the same bank, so they are read in ONE fused launch
   (up to ``mem_freq`` frames x HW queries) before being decoded frame by frame;
 * affinity, top-k softmax and the readout of all objects are one C-ABI call; ``aggregate_wbg`` is one kernel;
+* the key encoder and the decoder run once per segment on a batch of its frames (they only depend on the images
+  and on the bank), not once per frame;
 * the final per-frame argmax is one launch over all frames.
 
 ``prop_net`` may be this package's PropagationNetwork or the reference's own (same attribute names):
@@ -80,6 +82,9 @@ class InferenceCore:
         self.image_buf = {}
         self.interacted = set()
 
+        # batched encoder / decoder passes over the frames of a segment need this package's PropagationNetwork
+        # (decode_frames); a reference network passed in is driven frame by frame
+        self._batch_frames = hasattr(prop_net, "decode_frames")
         self._certain: MemoryBank | None = None
         top_k = getattr(getattr(prop_net, "memory", None), "top_k", 50)
         mem = getattr(prop_net, "memory", None)
@@ -109,6 +114,21 @@ class InferenceCore:
                 self.key_buf = {}
             self.key_buf[idx] = self.prop_net.encode_key(self.get_image_buffered(idx))
         return self.key_buf[idx]
+
+    def _key_feats(self, frames):
+        """Key features of several frames: the ones not cached yet go through the encoder as ONE batch (they only
+        depend on the images), then through the same cache, with the same flush policy, as get_key_feat_buffered."""
+        missing = [ti for ti in frames if ti not in self.key_buf]
+        if len(missing) > 1 and self._batch_frames:
+            batch = torch.cat([self.get_image_buffered(ti) for ti in missing], 0)
+            outs = self.prop_net.encode_key(batch)
+            for j, ti in enumerate(missing):
+                if len(self.key_buf) > self.k_buf_size:
+                    self.key_buf = {}
+                self.key_buf[ti] = tuple(o[j:j + 1] for o in outs)
+            if any(ti not in self.key_buf for ti in frames):   # the cache was flushed half-way: fall back
+                return [self.get_key_feat_buffered(ti) for ti in frames]
+        return [self.get_key_feat_buffered(ti) for ti in frames]
 
     # ------------------------------------------------------------------ pieces of segment_with_query
     def _decode(self, readout, qf8, qf4, qv16):
@@ -163,14 +183,20 @@ class InferenceCore:
                 if ti != end and abs(ti - last_ti) >= self.mem_freq:
                     break
             pos += len(seg)
-            feats = [self.get_key_feat_buffered(ti) for ti in seg]
+            feats = self._key_feats(seg)
             qk = torch.stack([f[0] for f in feats], 2) if len(seg) > 1 else feats[0][0]
             readout, _ = self._read(bank, qk)
             if len(seg) == 1:
                 readout = readout.unsqueeze(2)
+            decoded = None
+            if len(seg) > 1 and self._batch_frames:
+                # the frames of a segment are independent given the bank: one decoder pass for all of them
+                decoded = self.prop_net.decode_frames(readout, torch.cat([f[3] for f in feats], 0),
+                                                      torch.cat([f[4] for f in feats], 0),
+                                                      torch.cat([f[1] for f in feats], 0))
             for j, ti in enumerate(seg):
                 k16, qv16, qf16, qf8, qf4 = feats[j]
-                out_mask = self._decode(readout[:, :, j], qf8, qf4, qv16)
+                out_mask = decoded[j] if decoded is not None else self._decode(readout[:, :, j], qf8, qf4, qv16)
                 out_mask = aggregate_wbg(out_mask, keep_bg=True)
 
                 if ti != end and abs(ti - last_ti) >= self.mem_freq:

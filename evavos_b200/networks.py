@@ -247,6 +247,24 @@ class PropagationNetwork(nn.Module):
             return self.memory.read(mk16, qk16)
         return self.memory.read(mk16, qk16, mv16)
 
+    def decode_frames(self, readout, qf8, qf4, qv16):
+        """Batched ``decode`` for F query frames that were read against the same bank.
+
+        readout (K,512,F,H,W), qf8 / qf4 / qv16 with batch F -> (F,K,1,h,w) probabilities.  The same layers as
+        ``Decoder.forward`` (prop_net.py:13-30); the per-frame skip features, which the single-frame path broadcasts
+        over the K objects inside ``skip_conv(skip) + up``, are repeated explicitly so that one pass covers F*K maps.
+        """
+        k, _, f, hh, ww = readout.shape
+        dec = self.decoder
+        m4 = torch.cat([readout.permute(2, 0, 1, 3, 4), qv16.unsqueeze(1).expand(-1, k, -1, -1, -1)], 2)
+        x = dec.compress(m4.reshape(f * k, -1, hh, ww))
+        for block, skip in ((dec.up_16_8, qf8), (dec.up_8_4, qf4)):
+            up = F.interpolate(x, scale_factor=block.scale_factor, mode="bilinear", align_corners=False)
+            x = block.out_conv(block.skip_conv(skip).repeat_interleave(k, 0) + up)
+        x = dec.pred(F.relu(x))
+        x = F.interpolate(x, scale_factor=4, mode="bilinear", align_corners=False)
+        return torch.sigmoid(x).view(f, k, 1, *x.shape[-2:])
+
     def decode(self, readout, qf8, qf4, qv16):
         """readout (K,512,H,W) + shared query value feature -> (K,1,h,w) probabilities (prop_net.py:189-192)."""
         k = readout.shape[0]

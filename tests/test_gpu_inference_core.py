@@ -79,8 +79,11 @@ def test_reference_style_prop_net_is_accepted():
     a = ev.InferenceCore(prop, fuse, images, 1, mem_freq=2, device="cuda:0")
     b = ev.InferenceCore(Foreign(prop), fuse, images, 1, mem_freq=2, device="cuda:0")
     mask = torch.from_numpy(g["mask_0"])
-    assert np.array_equal(a.interact(mask, 0), b.interact(mask, 0))
-    assert torch.equal(a.prob, b.prob)
+    ma, mb = a.interact(mask, 0), b.interact(mask, 0)
+    # `a` runs the key encoder / decoder once per segment on a batch of frames, `b` frame by frame: the same layers,
+    # but cuDNN may pick another algorithm for another batch size, so agreement is to rounding, not bitwise
+    assert (a.prob - b.prob).abs().max().item() < 1e-3
+    assert (ma != mb).mean() < 1e-3
 
 
 def test_cpu_device_rejected():
