@@ -1,7 +1,7 @@
 """Quick on-GPU diagnostics: correctness of both selection paths vs the oracle and coarse timings.
 
-    python scripts/gpu_probe.py [--skip-tensor]
-Not a benchmark (bench.py is); prints enough detail to debug a failing path from one gpurun call.
+    python tests/gpu_probe.py [--skip-tensor]
+Checker tooling (it uses the oracle, so it lives under tests/); not a benchmark (bench.py is); prints enough detail to debug a failing path from one gpurun call.
 """
 import os
 import sys
