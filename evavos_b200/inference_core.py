@@ -85,6 +85,7 @@ class InferenceCore:
         # batched encoder / decoder passes over the frames of a segment need this package's PropagationNetwork
         # (decode_frames); a reference network passed in is driven frame by frame
         self._batch_frames = hasattr(prop_net, "decode_frames")
+        self.key_batch = 16   # frames per key-encoder pass when a whole propagation pass is encoded ahead
         self._certain: MemoryBank | None = None
         top_k = getattr(getattr(prop_net, "memory", None), "top_k", 50)
         mem = getattr(prop_net, "memory", None)
@@ -173,6 +174,14 @@ class InferenceCore:
         self._pass_bank = bank  # kept for inspection / tests; rebuilt every pass like the reference's locals
         last_ti = idx
         fuse = (closest_ti != self.t) and (closest_ti != -1)
+
+        # key features only depend on the images: encode the frames of this pass ahead of time in larger batches,
+        # as long as they all fit in the key-feature cache (k_buf_size, the reference's flush-all policy)
+        if self._batch_frames:
+            ahead = [ti for ti in this_range if ti not in self.key_buf]
+            if len(self.key_buf) + len(ahead) <= self.k_buf_size:
+                for c in range(0, len(ahead), self.key_batch):
+                    self._key_feats(ahead[c:c + self.key_batch])
 
         pos = 0
         while pos < len(this_range):
