@@ -50,10 +50,21 @@ namespace {
 constexpr int kStages = 8;
 constexpr int kAccStages = 3;   // 3 x 128 accumulator columns; the query operand lives in columns [384, 424)
 constexpr int kQueryCol = 384;
-constexpr int kThreads = 640;
-constexpr int kEpiThreads = 512;
+// Epilogue organisation (EVAVOS_GROUPS):
+//   1: 16 warps visit every tile in lock-step, 32 accumulator columns each; two MMA issuer warps.
+//   2: two groups of 8 warps serve even / odd tiles, 64 columns per warp as 2 x 32; one in-order MMA issuer.
+//   3: three groups of 8 warps, group g owns accumulator stage g (iterations i = g mod 3), 64 columns per warp as
+//      4 x 16 so that a thread fits in 72 registers and 28 warps are resident; one in-order MMA issuer.
+#ifndef EVAVOS_GROUPS
+#define EVAVOS_GROUPS 2
+#endif
+constexpr int kNumGroups = EVAVOS_GROUPS;
+constexpr int kEpiWarps = kNumGroups == 3 ? 24 : 16;
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kThreads = 128 + kEpiThreads;
 constexpr int kProducers = 4;   // TMA-issuing lanes of warp 0 (kStages % kProducers == 0)
-constexpr int kCols = 32;       // accumulator columns per epilogue thread
+constexpr int kCols = kNumGroups == 3 ? 16 : 32;   // accumulator columns per tcgen05.ld and epilogue thread
+constexpr int kClasses = kNumGroups == 3 ? 96 : 128;   // column classes per query and chunk (sweep 1)
 // Scores per staged hit group (sweep 2 tests one maximum per group).  Measured, filter time in us for 4 | 8:
 // cfg2 (32 k positions, a hit in 23 % | 40 % of the warp-groups) 43.8 | 52.7, cfg4 (324 k positions) 168.8 | 162.9.
 #ifndef EVAVOS_GROUP
@@ -61,10 +72,7 @@ constexpr int kCols = 32;       // accumulator columns per epilogue thread
 #endif
 constexpr int kGroup = EVAVOS_GROUP;
 constexpr int kPend = 8 + kCols / kGroup;  // staged hit groups per epilogue thread (flushed when more than 8 wait)
-#ifndef EVAVOS_SPLIT
-#define EVAVOS_SPLIT 1
-#endif
-constexpr bool kSplit = EVAVOS_SPLIT != 0;   // epilogue warp groups on alternate tiles (see the epilogue)
+constexpr bool kSplit = kNumGroups > 1;   // epilogue warp groups on different tiles (see the epilogue)
 constexpr int kBarBytes = 256;
 constexpr int kSmemBytes = kTileBytes * kStages + kBarBytes + 1024;
 
@@ -156,6 +164,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
+  if constexpr (kCols == 16) tmem_ld16(taddr, v);
+  else tmem_ld32(taddr, v);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -270,7 +292,7 @@ __device__ __forceinline__ void warp_threshold(const PassParams& p, int64_t q, i
       for (int u = 0; u < 8; ++u)
 #pragma unroll
         for (int t = 0; t < 4; ++t)
-          w[u][t] = (g + u < p.n_chunks) ? __ldcg(row0 + (g + u) * chunk_stride + 32 * t) : kEmptyNh;
+          w[u][t] = (g + u < p.n_chunks && 32 * t < kClasses) ? __ldcg(row0 + (g + u) * chunk_stride + 32 * t) : kEmptyNh;
 #pragma unroll
       for (int u = 0; u < 8; ++u)
 #pragma unroll
@@ -362,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
     }
     for (int a = 0; a < kAccStages; ++a) {
       mbar_init(bar_acc_full + 8 * a, 1);
-      mbar_init(bar_acc_empty + 8 * a, kSplit ? kEpiThreads / 64 : kEpiThreads / 32);
+      mbar_init(bar_acc_empty + 8 * a, kSplit ? 8 : kEpiWarps);   // warps that visit one tile
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -469,14 +491,16 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
     const int quarter = ew & 3;           // TMEM lane quarter this warp may access
     const int grp = kSplit ? (ew >> 3) : 0;
     const int colbase = kSplit ? ((ew >> 2) & 1) * 64 : (ew >> 2) * kCols;
-    constexpr int kBlocks = kSplit ? 2 : 1;   // 32-column loads per visited tile
+    constexpr int kBlocks = kSplit ? 64 / kCols : 1;   // tcgen05.ld blocks per visited tile
     const int row = quarter * 32 + lane;
     const int et = threadIdx.x - 128;
     const int64_t q = (int64_t)m_tile * 128 + row;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    // first sweep-1 iteration of this warp and its stride
-    const int i_first = kSplit ? ((((t0 & 1) == grp) ? 0 : 1)) : 0;
-    constexpr int i_step = kSplit ? 2 : 1;
+    // iterations this warp visits: 2 groups - tiles of the group's parity; 3 groups - i = grp (mod 3), i.e. always
+    // accumulator stage `grp`, in both sweeps; lock-step - all
+    constexpr int i_step = kSplit ? kNumGroups : 1;
+    const int i_first = kNumGroups == 3 ? grp : (kNumGroups == 2 ? ((((t0 & 1) == grp) ? 0 : 1)) : 0);
+    const int i_first2 = kNumGroups == 3 ? n_tiles + (grp + 3 - n_tiles % 3) % 3 : n_tiles + i_first;
 
     // visit(i, math): wait for accumulator tile i, read this warp's columns block by block (the stage goes back to
     // the MMA warps as soon as the last block is in registers) and call math(block, values, first position).
@@ -489,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
       for (int blk = 0; blk < kBlocks; ++blk) {
         float v[kCols];
         if constexpr (!(EVAVOS_EXP & 1)) {
-          tmem_ld32(lane_addr + (uint32_t)(a * 128 + colbase + blk * kCols), v);
+          tmem_ld_cols(lane_addr + (uint32_t)(a * 128 + colbase + blk * kCols), v);
           tmem_ld_wait();
         } else {
           for (int j = 0; j < kCols; ++j) v[j] = kEmptyNh;
@@ -510,9 +534,10 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
       // Column classes per thread: 16 x (columns j and j + 16 of a 32-column block), one set per block (kSplit: of
       // the tiles of this group's parity) or per tile parity (lock-step) - 128 per query and chunk either way.  Any
       // partition of the positions into classes gives a valid bound; this one costs one FMNMX3 per two scores.
-      float cmax[kCols];
+      constexpr int kOwn = 32;   // class maxima held per thread
+      float cmax[kOwn];
 #pragma unroll
-      for (int j = 0; j < kCols; ++j) cmax[j] = kEmptyNh;
+      for (int j = 0; j < kOwn; ++j) cmax[j] = kEmptyNh;
       auto class_max = [&](float* cm, const float* v, int64_t n0) {
         int pending = 0;
         if constexpr ((EVAVOS_EXP & 2) != 0) {
@@ -525,7 +550,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
       };
       if constexpr (kSplit) {
         for (int i = i_first; i < n_tiles; i += i_step)
-          visit(i, [&](int blk, const float* v, int64_t n0) { class_max(blk == 0 ? cmax : cmax + kCols / 2, v, n0); });
+          visit(i, [&](int blk, const float* v, int64_t n0) { class_max(cmax + blk * (kCols / 2), v, n0); });
       } else {
         int i = 0;   // parity of the tile's index in the bank, not in the chunk
         if (t0 & 1) visit(i++, [&](int, const float* v, int64_t n0) { class_max(cmax + kCols / 2, v, n0); });
@@ -534,10 +559,19 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
           if (i + 1 < n_tiles) visit(i + 1, [&](int, const float* v, int64_t n0) { class_max(cmax + kCols / 2, v, n0); });
         }
       }
-      float4* dst = reinterpret_cast<float4*>(p.class_max + ((int64_t)chunk * p.nq_pad + q) * 128 + (ew >> 2) * kCols);
+      if constexpr (kNumGroups == 3) {
+        // 6 (group, half) slots of 16 classes: neighbouring classes of a thread are merged pairwise (96 per query)
+        float4* dst = reinterpret_cast<float4*>(p.class_max + ((int64_t)chunk * p.nq_pad + q) * 128 + (ew >> 2) * 16);
 #pragma unroll
-      for (int j4 = 0; j4 < kCols / 4; ++j4)
-        dst[j4] = make_float4(cmax[j4 * 4], cmax[j4 * 4 + 1], cmax[j4 * 4 + 2], cmax[j4 * 4 + 3]);
+        for (int j4 = 0; j4 < 4; ++j4)
+          dst[j4] = make_float4(fmaxf(cmax[8 * j4], cmax[8 * j4 + 1]), fmaxf(cmax[8 * j4 + 2], cmax[8 * j4 + 3]),
+                                fmaxf(cmax[8 * j4 + 4], cmax[8 * j4 + 5]), fmaxf(cmax[8 * j4 + 6], cmax[8 * j4 + 7]));
+      } else {
+        float4* dst = reinterpret_cast<float4*>(p.class_max + ((int64_t)chunk * p.nq_pad + q) * 128 + (ew >> 2) * 32);
+#pragma unroll
+        for (int j4 = 0; j4 < kOwn / 4; ++j4)
+          dst[j4] = make_float4(cmax[j4 * 4], cmax[j4 * 4 + 1], cmax[j4 * 4 + 2], cmax[j4 * 4 + 3]);
+      }
     }
 
     // ---- thresholds: every CTA of a query tile takes a slice of its 128 rows ----
@@ -563,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
       int32_t* pp = p.pend_pos + (int64_t)blockIdx.x * kPend * kEpiThreads + et;
       int pending = 0;
       float unused[1];
-      for (int i = n_tiles + i_first; i < n_iter; i += i_step) {
+      for (int i = i_first2; i < n_iter; i += i_step) {
         visit(i, [&](int, const float* v, int64_t n0) {
           if constexpr ((EVAVOS_EXP & 2) != 0) {
           } else if (n0 + kCols > p.n_pos) {
