@@ -55,6 +55,9 @@ constexpr int kQueryCol = 384;
 //   2: two groups of 8 warps serve even / odd tiles, 64 columns per warp as 2 x 32; one in-order MMA issuer.
 //   3: three groups of 8 warps, group g owns accumulator stage g (iterations i = g mod 3), 64 columns per warp as
 //      4 x 16 so that a thread fits in 72 registers and 28 warps are resident; one in-order MMA issuer.
+#ifndef EVAVOS_RARE
+#define EVAVOS_RARE (-1)   // -1: decide per launch from the bank size; 0 / 1: force (timing experiments)
+#endif
 #ifndef EVAVOS_GROUPS
 #define EVAVOS_GROUPS 2
 #endif
@@ -201,6 +204,7 @@ struct PassParams {
   unsigned int* grid_counter;  // one counter per query tile of the launch, zeroed before every launch
   int m_tile0;          // first query tile of this launch
   int top_k;
+  int rare_hits;        // sweep 2 tests a whole block before its groups (see the epilogue)
 };
 
 // Sweep 2 stages every group of kGroup adjacent scores whose maximum reaches the threshold (scores + first
@@ -604,7 +608,16 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
             const int valid = (int)max((int64_t)0, p.n_pos - n0);
             consume_tile<2, true>(v, unused, thr, (int32_t)n0, valid, ps, pp, pending);
           } else {
-            consume_tile<2, false>(v, unused, thr, (int32_t)n0, kCols, ps, pp, pending);
+            // banks where a hit is rare per block: one maximum over the whole block first, the per-group test only
+            // when it reaches the threshold (the branch is warp-divergent, but most warps skip the block)
+            bool look = true;
+            if (p.rare_hits) {
+              float m = v[0];
+#pragma unroll
+              for (int j = 1; j < kCols; ++j) m = fmaxf(m, v[j]);
+              look = m >= thr;
+            }
+            if (look) consume_tile<2, false>(v, unused, thr, (int32_t)n0, kCols, ps, pp, pending);
           }
           if (pending > kPend - kCols / kGroup) {  // the next block stages at most kCols / kGroup groups
             flush_pending(ps, pp, pending, thr, p.cand, p.cand_cnt, q);
@@ -678,6 +691,9 @@ int launch_score_select(const float* query, int64_t query_ch_stride, const void*
     p.grid_counter = grid_counter;
     p.m_tile0 = m0;
     p.top_k = top_k;
+    // expected candidates per query ~ 1.4 top_k, a block is 32 lanes x kCols scores: rare = a block holds a hit
+    // with probability below ~1/2
+    p.rare_hits = (EVAVOS_RARE >= 0) ? EVAVOS_RARE : ((double)n_pos > 2.0 * 1.4 * top_k * 32.0 * kCols ? 1 : 0);
     const unsigned grid = (unsigned)(p.n_mtiles * n_chunks);
     p.pend_score = reinterpret_cast<float4*>(pending);
     p.pend_pos = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(pending) +
