@@ -1,31 +1,38 @@
 """bench.py - memory-read query-frames/s of the B200 space-time memory read (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg3|cfg4|cfg5]
 
-A step is one query frame of the hot path on synthetic inputs: key affinity + top-k softmax +
-value readout for all objects (the fused read) followed by the soft aggregation across objects.
-Workload (BASELINE.json configs[1]): DAVIS-17 480p, 30x54 feature map, 3 objects, 20-frame bank.
+A step is one query frame of the hot path on synthetic inputs: key affinity + top-k softmax + value readout for all
+objects (one evavos_memread call: filter, finalize, readout kernels) followed by the soft aggregation across objects.
+Default workload (BASELINE.json configs[1]): DAVIS-17 480p, 30x54 feature map, 3 objects, 20-frame bank.
 
- * value  - whole-job query-frames/s with the bank resident in HBM (CUDA events, max over ranks).
-            Four banks (each > L2 together) are rotated so no step finds its inputs in L2.
- * e2e    - the same step through the public API with pinned HOST buffers, synchronised every step.  The bank
-            is engine state (exactly as the reference keeps its bank resident in host memory between frames); a
-            step's inputs are the frame's query key, the decoder probabilities and - every mem_freq-th frame -
-            one new memory frame (H2D + in-place append, inference_core.py:174-177); its result is the readout
-            and the aggregated probabilities (D2H).  `e2e_full_upload` is the stateless variant
-            (evavos_memread_host: the whole bank crosses PCIe every step).
- * roofline - the dominant kernel (sparse readout, HBM-bound), timed with CUDA events inside the
-            timed region; algorithmic bytes = s*K*CV*min(N, k*HW) + 4*K*CV*HW + 8*k*HW.
- * cpu_baseline / --impl reference - oracle/torch_port.py (op-for-op port of the reference's dense
-            torch path; /root/reference is not on the GPU box) on all host cores.
-Multi-GPU (torchrun, one rank per GPU): independent videos are partitioned across ranks with no
-collective -> weak scaling; value = N * K / max-over-ranks time.
-`--workload cfg4` is the long-video case instead: ONE 200-frame bank sharded along the memory axis over
-the ranks (NCCL all-gather of top-k candidates + all-reduce of partial readouts) -> strong scaling.
+ONE JSON line:
+ * value      whole-job query-frames/s with the banks resident in HBM (CUDA events, max over ranks); four banks
+              (together > L2) are rotated so no step finds its inputs in L2.  `batched_read` is the same workload the
+              way the product issues it (inference_core.py: the mem_freq = 5 query frames between two memory appends
+              share one launch).
+ * roofline   one entry per kernel of the step (`kernels`), the whole step against SURVEY 8(d)'s T_roof (`step`), and
+              at top level the DOMINANT (longest) kernel.  Kernel times come from a second, instrumented pass over the
+              same steps (CUDA events between the kernels, recorded by the library: evavos_stage_timing); the event
+              records defeat the kernels' programmatic-dependent-launch overlap, so they add up to more than
+              ms_per_step.  Readout bytes count the DISTINCT value rows the step selected (measured).
+ * gpu_baseline  the reference's own torch op sequence (oracle/torch_port.py: SGEMM + 3 elementwise passes, topk,
+              scatter, one bmm per object, 6-8 elementwise aggregate launches) on CUDA tensors on the same B200 - the
+              "existing GPU path" (SURVEY 8d).  Checker code, timed beside the product, never called by it.
+ * e2e        the same step through the public API with pinned HOST buffers (streaming: the bank is engine state);
+              `e2e_full_upload` is the stateless evavos_memread_host form.
+ * cpu_baseline / --impl reference   oracle/torch_port.py on all host cores (/root/reference is not on the GPU box).
+ * N == 1 also carries `cfg4` and `cfg5`: BASELINE.json configs[3] (unsharded, one GPU) and configs[4] (bf16 values)
+   with their own stage times, rooflines and GPU baselines.
+ * N > 1: ranks run independent videos (no collective, weak scaling: the headline line), and the line also carries
+   `sharded_cfg4`: ONE 200-frame bank sharded along the memory axis over the N ranks (NCCL exchange) with per-rank
+   stage times, the same run's single-GPU time of the same read, the efficiency between the two, and `parity_ok`
+   (rank 0's sharded result against its own single-bank read).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -42,14 +49,14 @@ WORKLOADS = {
     # name: (CK, CV, T, H, W, K objects, seed, description)
     "cfg1": (64, 512, 5, 30, 54, 1, 1235, "DAVIS-17 480p (30x54), 1 object, 5-frame bank"),
     "cfg2": (64, 512, 20, 30, 54, 3, 1236, "DAVIS-17 480p (30x54), 3 objects, 20-frame bank, top-50 readout + soft aggregation"),
-    "cfg4": (64, 512, 200, 30, 54, 1, 1238, "MOSE-style long video 480p, 1 object, 200-frame bank (unsharded)"),
+    "cfg4": (64, 512, 200, 30, 54, 1, 1238, "MOSE-style long video 480p, 1 object, 200-frame bank"),
     "cfg3": (64, 512, 32, 30, 54, 1, 1237, "independent synthetic 480p videos (32 frames, 1 object), full key/value encode + memory read + decode"),
     "cfg5": (64, 512, 50, 68, 120, 5, 1239, "1080p-equivalent feature map (68x120), 5 objects, 50-frame bank, bf16 value bank"),
 }
 TOP_K = 50
 N_BANKS = 4
-FRAMES_PER_EXCHANGE = 5   # query frames between two memory appends (mem_freq) read in one sharded exchange
-KERNELS_PER_STEP = 5  # fused score filter, exact fallback (overflow), finalize, readout, aggregate (+ one memset node)
+MEM_FREQ = 5              # query frames between two memory appends (inference_core.py:174): read in one launch
+KERNELS_PER_STEP = 4      # score_select_kernel, finalize_kernel, readout kernel, aggregate_kernel (+ one memset node)
 
 
 def synth(seed, ck, cv, t, h, w, k):
@@ -61,13 +68,13 @@ def synth(seed, ck, cv, t, h, w, k):
 
 
 def peaks():
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
-        with open(path) as f:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        return {"hbm": float(p["hbm_gbs"]), "tc": float(p["bf16_tflops_sustained"]), "tc_burst": float(p["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json; bf16 = sustained figure, the kernels run inside a long step)"}
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md)"
+        return {"hbm": 6650.0, "tc": 1400.0, "tc_burst": 1590.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler:
@@ -103,6 +110,7 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+# ----------------------------------------------------------------------------------------------- CPU reference arm
 def cpu_reference_rate(cfg, steps, warmup, budget_s=150.0):
     """Reference dense torch path (oracle/torch_port.py) on all host cores; returns (qf/s, info)."""
     from oracle import torch_port as port
@@ -154,158 +162,302 @@ def run_reference(args, cfg, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def run_sharded(args, cfg, rank, world, local_rank):
-    """cfg4: one long bank sharded by frame over the ranks; strong scaling (total work fixed)."""
+# ----------------------------------------------------------------------------------------------- helpers (GPU)
+def time_loop(fn, steps, warmup, stream, dev):
+    """ms for `steps` calls of fn(i) after `warmup`, CUDA events on the launching stream."""
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
+        fn(i)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1)
+
+
+def stage_pass(read_fn, agg_fn, steps, stream, dev):
+    """Instrumented pass: mean us of {filter, finalize, readout} (library events) and of the aggregate kernel."""
+    from evavos_b200 import _lib
+    lib = _lib.load()
+    steps = min(steps, 200)
+    lib.evavos_stage_timing(1)
+    ev = []
+    for i in range(steps):
+        read_fn(i)
+        if agg_fn is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            agg_fn(i)
+            b.record(stream)
+            ev.append((a, b))
+    ms = (ctypes.c_float * 4)()
+    _lib.check(lib.evavos_stage_timing_read(ms))
+    lib.evavos_stage_timing(0)
+    torch.cuda.synchronize(dev)
+    out = {"filter": ms[0] * 1e3, "finalize": ms[2] * 1e3, "readout": ms[3] * 1e3}
+    if ev:
+        out["aggregate"] = 1e3 * sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+    return out
+
+
+def rooflines(shape, stages_us, step_us, distinct_rows, val_bytes, pk, frames=1):
+    """Per-kernel roofline entries + the whole step.  Returns (dominant, kernels, step)."""
+    ck, cv, n_pos, hw, k_obj, agg_px = shape
+    nq = hw * frames
+    kernels = {}
+    f_filter = 2.0 * n_pos * nq * ck
+    us = stages_us["filter"]
+    kernels["score_select_kernel"] = {
+        "bound": "tensor", "us_per_launch": us, "algorithmic_flops": f_filter, "achieved": f_filter / us / 1e6,
+        "peak": pk["tc"], "unit": "TFLOP/s", "frac": f_filter / us / 1e6 / pk["tc"],
+        "note": "2*N*HW*CK: ONE pass of the 64-channel contraction; the kernel contracts 1 + 1/sample_stride sweeps and a 5th K=16 slice for -|k|^2/2"}
+    b_fin = float(nq) * TOP_K * (4 * ck + 8 + 8)
+    us = stages_us["finalize"]
+    kernels["finalize_kernel"] = {
+        "bound": "hbm", "us_per_launch": us, "algorithmic_bytes": b_fin, "achieved": b_fin / us / 1e3, "peak": pk["hbm"],
+        "unit": "GB/s", "frac": b_fin / us / 1e3 / pk["hbm"],
+        "note": "k exact key rows + k list entries + k outputs per query; latency-bound (dependent gathers), not bandwidth-bound"}
+    b_ro = float(val_bytes) * k_obj * cv * distinct_rows + 4.0 * k_obj * cv * nq + 8.0 * TOP_K * nq
+    us = stages_us["readout"]
+    kernels["readout_kernel"] = {
+        "bound": "hbm", "us_per_launch": us, "algorithmic_bytes": b_ro, "achieved": b_ro / us / 1e3, "peak": pk["hbm"],
+        "unit": "GB/s", "frac": b_ro / us / 1e3 / pk["hbm"], "distinct_value_rows": int(distinct_rows),
+        "note": "every DISTINCT selected value row once (measured count) + output once + (idx, weight) once"}
+    if "aggregate" in stages_us:
+        b_ag = float(2 * k_obj + 1) * agg_px * 4 * frames
+        us = stages_us["aggregate"]
+        kernels["aggregate_kernel"] = {
+            "bound": "hbm", "us_per_launch": us / frames, "algorithmic_bytes": b_ag / frames, "achieved": b_ag / us / 1e3,
+            "peak": pk["hbm"], "unit": "GB/s", "frac": b_ag / us / 1e3 / pk["hbm"]}
+    # whole step, SURVEY 8(d): F_alg = key contraction + sparse readout; B_alg = each needed input once + outputs once
+    f_alg = f_filter + 2.0 * k_obj * cv * TOP_K * nq
+    s_key = 2.0 if val_bytes == 2 else 4.0
+    b_alg = s_key * (n_pos * ck + nq * ck) + val_bytes * k_obj * cv * min(n_pos, TOP_K * nq) + 4.0 * k_obj * cv * nq
+    b_alg_distinct = b_alg - val_bytes * k_obj * cv * (min(n_pos, TOP_K * nq) - distinct_rows)
+    if "aggregate" in stages_us:
+        b_alg += (2 * k_obj + 1) * agg_px * 4.0 * frames
+        b_alg_distinct += (2 * k_obj + 1) * agg_px * 4.0 * frames
+    t_tc, t_hbm = f_alg / pk["tc"] / 1e6, b_alg / pk["hbm"] / 1e3
+    t_roof = max(t_tc, t_hbm)
+    step = {"t_roof_us": t_roof, "t_tensor_us": t_tc, "t_hbm_us": t_hbm, "bound": "tensor" if t_tc > t_hbm else "hbm",
+            "us": step_us, "frac": t_roof / step_us, "algorithmic_flops": f_alg, "algorithmic_bytes": b_alg,
+            "frac_with_distinct_rows": max(t_tc, b_alg_distinct / pk["hbm"] / 1e3) / step_us,
+            "note": "SURVEY.md 8(d): max(F_alg / P_tc, B_alg / BW_hbm) over the measured (un-instrumented) step time"}
+    name = max(kernels, key=lambda n: kernels[n]["us_per_launch"] * (frames if n == "aggregate_kernel" else 1))
+    dom = dict(kernels[name])
+    dom["kernel"] = name
+    return dom, kernels, step
+
+
+def build_banks(cfg, dev, n_banks, seed_shift=0, bf16=False, on_device=False):
+    import evavos_b200 as ev
+    ck, cv, t, h, w, k, seed, _ = cfg
+    banks, queries = [], []
+    for b in range(n_banks):
+        vd = torch.bfloat16 if bf16 else torch.float32
+        bank = ev.MemoryBank(k, ck, cv, h, w, t, dev, value_dtype=vd, keep_reference_layout=False)
+        if on_device:     # large banks: synthesised frame by frame on the device
+            g = torch.Generator(device=dev).manual_seed(seed + 100 * b + seed_shift)
+            for f in range(t):
+                kf = torch.randn(1, ck, h, w, generator=g, device=dev)
+                vf = torch.randn(k, cv, 1, h, w, generator=g, device=dev)
+                if bf16:
+                    kf, vf = kf.to(torch.bfloat16).float(), vf.to(torch.bfloat16).float()
+                bank.append(kf, vf)
+            q = torch.randn(1, ck, MEM_FREQ, h, w, generator=g, device=dev)
+            q = q.to(torch.bfloat16).float() if bf16 else q
+        else:
+            mk, qk, mv = synth(seed + 100 * b + seed_shift, ck, cv, t, h, w, k)
+            for f in range(t):  # built the way do_pass builds it: one append per memory frame
+                bank.append(mk[:, :, f].to(dev), mv[:, :, f:f + 1].to(dev))
+            g = torch.Generator().manual_seed(seed + 100 * b + seed_shift + 7)
+            q = torch.cat([qk.unsqueeze(2), torch.randn(1, ck, MEM_FREQ - 1, h, w, generator=g)], 2).to(dev)
+        banks.append(bank)
+        queries.append(q)
+    return banks, queries
+
+
+def gpu_baseline(cfg, bank_tensors, steps, dev, stream, with_aggregate=True):
+    """The reference's own torch sequence on CUDA tensors (oracle/torch_port.py, bit-equal to the reference on CPU)."""
+    from oracle import torch_port as port
+    ck, cv, t, h, w, k, seed, _ = cfg
+    mk, qk, mv = bank_tensors
+    prob = torch.rand(k, 1, h * 16, w * 16, device=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False      # the reference's default: true fp32 matmul / bmm
+
+    def step(i):
+        out = port.memory_read(mk, qk, mv, TOP_K)
+        if with_aggregate:
+            port.aggregate_wbg(prob, keep_bg=True)
+        return out
+
+    ms = time_loop(step, steps, 2, stream, dev)
+    return {"value": steps / (ms * 1e-3), "unit": "query-frames/s", "ms_per_step": ms / steps, "steps": steps,
+            "impl": "oracle/torch_port.py (the reference's ATen op sequence) on CUDA tensors, fp32, allow_tf32=False",
+            "launches_per_step": "~%d" % (12 + k + (8 if with_aggregate else 0))}
+
+
+def side_workload(name, args, dev, stream, pk, want_baseline=True):
+    """cfg4 / cfg5 on one GPU: value, stage times, rooflines, GPU baseline (extra keys of the N=1 line)."""
+    import evavos_b200 as ev
+    cfg = WORKLOADS[name]
+    ck, cv, t, h, w, k, seed, desc = cfg
+    bf16 = name == "cfg5"
+    hw, n_pos = h * w, t * h * w
+    banks, queries = build_banks(cfg, dev, 2, bf16=bf16, on_device=True)
+    steps = max(5, min(args.steps, 20))
+    res = {"workload": name + ": " + desc, "dtype": "bf16 values + bf16-representable keys, fp32 accumulation" if bf16 else "f32",
+           "memory_positions": n_pos, "queries_per_frame": hw, "objects": k,
+           "l2": f"2 rotating banks of {banks[0].val_pm.numel() * banks[0].val_pm.element_size() / 1e9:.2f} GB values"}
+    for frames, key in ((1, "single_frame"), (MEM_FREQ, "batched_read")):
+        qs = [q[:, :, 0] if frames == 1 else q for q in queries]
+        outs = [torch.empty((k, cv, frames * hw), dtype=torch.float32, device=dev) for _ in range(2)]
+
+        def read(i):
+            return ev.memory_read(banks[i % 2], qs[i % 2], TOP_K, out=outs[i % 2].view(k, cv, *qs[i % 2].shape[2:]))
+
+        ms = time_loop(read, steps, 3, stream, dev)
+        stages = stage_pass(read, None, steps, stream, dev)
+        _, aff = ev.memory_read(banks[0], qs[0], TOP_K, want_readout=False, want_topk=True)
+        distinct = int(torch.unique(aff.idx).numel())
+        dom, kernels, step = rooflines((ck, cv, n_pos, hw, k, 0), stages, 1e3 * ms / steps, distinct, 2 if bf16 else 4, pk, frames)
+        res[key] = {"value": frames * steps / (ms * 1e-3), "unit": "query-frames/s", "ms_per_launch": ms / steps,
+                    "query_frames_per_launch": frames, "steps": steps, "stages_us": stages,
+                    "roofline": {"dominant": dom["kernel"], "kernels": kernels, "step": step}}
+    if want_baseline:
+        # the same bank as dense reference-layout tensors (rebuilt from the shadow: position-major -> (C,T,H,W))
+        b0 = banks[0]
+        mk = b0.key_pm[:n_pos].t().reshape(1, ck, t, h, w).contiguous()
+        mv = b0.val_pm[:, :n_pos].float().permute(0, 2, 1).reshape(k, cv, t, h, w).contiguous()
+        try:
+            res["gpu_baseline"] = gpu_baseline(cfg, (mk, queries[0][:, :, 0].contiguous(), mv), 3, dev, stream, with_aggregate=False)
+            res["gpu_baseline"]["speedup_single_frame"] = res["single_frame"]["value"] / res["gpu_baseline"]["value"]
+        except Exception as e:   # e.g. out of memory for the dense 13.3 GB affinity on a busy device
+            res["gpu_baseline"] = {"unavailable": repr(e)[:200]}
+        del mk, mv
+    del banks, queries
+    torch.cuda.empty_cache()
+    return res
+
+
+# ----------------------------------------------------------------------------------------------- sharded cfg4
+def run_sharded(args, cfg, rank, world, local_rank, dist=None, emit=True):
+    """cfg4: one long bank sharded by frame over the ranks; strong scaling (total work fixed).
+
+    Returns the result dict (rank 0) - printed as its own line only with --workload cfg4."""
     import evavos_b200 as ev
     from evavos_b200.sharded import ShardedMemoryBank
     ck, cv, t, h, w, k, seed, desc = cfg
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    dist = None
-    if world > 1:
+    own_pg = False
+    if world > 1 and dist is None:
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
+        own_pg = True
     hw, n_pos = h * w, t * h * w
     n_banks = 2
-    banks, queries = [], []
+    steps = max(5, min(args.steps, 50))
+    banks, full, queries = [], [], []
     for b in range(n_banks):
-        g = torch.Generator().manual_seed(seed + 100 * b)
+        g = torch.Generator(device=dev).manual_seed(seed + 100 * b)      # the same stream of frames on every rank
         bank = ShardedMemoryBank(k, ck, cv, h, w, t, dev)
-        for f in range(t):                      # same frames on every rank; only the owner keeps one
-            kf = torch.randn(1, ck, h, w, generator=g)
-            vf = torch.randn(k, cv, 1, h, w, generator=g)
-            if bank.owner_of(f) == rank:
-                bank.append(kf.to(dev), vf.to(dev))
-            else:
-                bank.n_frames += 1
+        whole = ev.MemoryBank(k, ck, cv, h, w, t, dev, keep_reference_layout=False) if b == 0 else None
+        for f in range(t):
+            kf = torch.randn(1, ck, h, w, generator=g, device=dev)
+            vf = torch.randn(k, cv, 1, h, w, generator=g, device=dev)
+            bank.append(kf, vf)                                           # only the owner keeps it
+            if whole is not None:
+                whole.append(kf, vf)
         banks.append(bank)
-        queries.append(torch.randn(1, ck, FRAMES_PER_EXCHANGE, h, w, generator=g).to(dev))
-    prob = torch.rand(k, 1, h * 16, w * 16, device=dev)
+        full.append(whole)
+        queries.append(torch.randn(1, ck, MEM_FREQ, h, w, generator=g, device=dev))
     stream = torch.cuda.current_stream(dev)
 
     def step(i):
         # mem_freq = 5 query frames share one bank state (inference_core.py:174): one exchange for all of them
-        out = banks[i % n_banks].read(queries[i % n_banks], TOP_K)
-        aggs = [ev.aggregate_wbg(prob, keep_bg=True) for _ in range(FRAMES_PER_EXCHANGE)]
-        return out, aggs
+        return banks[i % n_banks].read(queries[i % n_banks], TOP_K)
 
-    for i in range(args.warmup):
+    def step_single(i):
+        return ev.memory_read(full[0], queries[i % n_banks], TOP_K)[0]
+
+    # parity: every rank's sharded result against its own single-bank read of the same bank
+    out_s, idx_s, w_s = banks[0].read(queries[0], TOP_K, return_topk=True)
+    out_1, aff_1 = ev.memory_read(full[0], queries[0], TOP_K, want_topk=True)
+    torch.cuda.synchronize(dev)
+    rel = float(((out_s - out_1).norm() / out_1.norm()).item())
+    same_idx = bool(torch.equal(idx_s, aff_1.idx))
+    parity = torch.tensor([1.0 if (rel < 1e-5 and same_idx) else 0.0, rel], device=dev, dtype=torch.float64)
+
+    for i in range(max(3, args.warmup)):
         step(i)
     torch.cuda.synchronize(dev)
     if dist:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     torch.cuda.synchronize(dev)
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record(stream)
-    for i in range(args.steps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
         step(i)
-    t1.record(stream)
+    e1.record(stream)
     torch.cuda.synchronize(dev)
     if dist:
         dist.barrier()
-    elapsed_ms = t0.elapsed_time(t1)
-    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = e0.elapsed_time(e1)
+    single_ms = time_loop(step_single, steps, 3, stream, dev)
+    stage_us = banks[0].profile(queries[0], TOP_K, reps=10) if hasattr(banks[0], "profile") else {}
     if dist:
-        tm = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        tm = torch.tensor([elapsed_ms, single_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(tm.item())
+        elapsed_ms, single_ms = float(tm[0].item()), float(tm[1].item())
+        dist.all_reduce(parity, op=dist.ReduceOp.MIN if False else dist.ReduceOp.MAX)   # worst rel error
+        ok = torch.tensor([1.0 if (rel < 1e-5 and same_idx) else 0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        parity_ok = bool(ok.item() > 0.5)
+        st = torch.tensor([stage_us.get(n, 0.0) for n in sorted(stage_us)], device=dev, dtype=torch.float64)
+        if st.numel():
+            dist.all_reduce(st, op=dist.ReduceOp.MAX)
+            stage_us = {n: float(v) for n, v in zip(sorted(stage_us), st.tolist())}
+    else:
+        parity_ok = bool(rel < 1e-5 and same_idx)
+    res = None
     if rank == 0:
-        value = FRAMES_PER_EXCHANGE * args.steps / (elapsed_ms * 1e-3)
-        flops = 2.0 * n_pos * hw * ck * FRAMES_PER_EXCHANGE                       # the one unavoidable dense contraction (SURVEY.md 8d)
-        t_tc = flops / 1390.2e12
-        line = {
+        value = MEM_FREQ * steps / (elapsed_ms * 1e-3)
+        single = MEM_FREQ * steps / (single_ms * 1e-3)
+        flops = 2.0 * n_pos * hw * ck * MEM_FREQ
+        pk = peaks()
+        res = {
             "metric": "memory-read query-frames/sec", "value": value, "unit": "query-frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + desc + f", memory axis sharded by frame over {world} GPU(s)",
-                       "top_k": TOP_K, "memory_positions": n_pos, "queries_per_frame": hw, "objects": k,
-                       "query_frames_per_step": FRAMES_PER_EXCHANGE,
-                       "l2": f"{n_banks} rotating banks, {n_banks * 4 * (k * cv + ck) * n_pos / 1e6:.0f} MB of inputs > 126 MB L2",
-                       "parallelism": f"memory-axis shards x{world}, all-gather(top-k) + all-reduce(readout)"},
-            "clocks": clocks, "gpu_launches": (KERNELS_PER_STEP + 1 + FRAMES_PER_EXCHANGE - 1) * args.steps,
-            "roofline": {"bound": "tensor", "kernel": "whole sharded read (score filter dominates)", "achieved": flops / (elapsed_ms / args.steps * 1e-3) / 1e12 / world,
-                         "peak": 1390.2, "unit": "TFLOP/s", "frac": t_tc / world / (elapsed_ms / args.steps * 1e-3), "traffic": None,
+            "steps": steps, "ms_per_step": elapsed_ms / steps, "scaling": "strong", "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg4: " + desc + f", memory axis sharded by frame over {world} GPU(s)", "top_k": TOP_K,
+                       "memory_positions": n_pos, "queries_per_frame": hw, "objects": k, "query_frames_per_step": MEM_FREQ,
+                       "parallelism": f"memory-axis shards x{world}", "exchange": getattr(banks[0], "exchange_desc", "all-gather(top-k) + all-reduce(readout)")},
+            "single_gpu_same_run": {"value": single, "ms_per_step": single_ms / steps,
+                                    "note": "the same 5-frame read against the whole bank on ONE GPU, timed in this run"},
+            "efficiency_vs_same_run_single_gpu": value / (world * single),
+            "speedup_vs_same_run_single_gpu": value / single,
+            "per_rank_stage_us_max": stage_us,
+            "parity_ok": parity_ok, "parity_rel_l2_max": float(parity[1].item()),
+            "roofline": {"bound": "tensor", "kernel": "whole sharded read", "achieved": flops / (elapsed_ms / steps * 1e-3) / 1e12 / world,
+                         "peak": pk["tc"], "unit": "TFLOP/s", "frac": flops / pk["tc"] / 1e12 / world / (elapsed_ms / steps * 1e-3),
                          "note": "algorithmic flops 2*N*HW*CK per query frame over the measured step time, per GPU"},
         }
-        print(json.dumps(line), flush=True)
-    if dist:
+        if emit:
+            line = dict(res)
+            line.update({"warmup": args.warmup, "higher_is_better": True, "vs_baseline": None,
+                         "gpu_launches": (3 + 2) * steps})
+            print(json.dumps(line), flush=True)
+    del banks, full, queries
+    torch.cuda.empty_cache()
+    if own_pg:
         dist.destroy_process_group()
+    return res
 
 
-def run_cfg5(args, cfg, rank, world, local_rank):
-    """BASELINE.json configs[4] on one GPU per rank (independent replicas): bf16-representable inputs, bf16 value
-    shadow, fp32 accumulation.  Banks are synthesised frame by frame on the device (10 GB of fp32 values per
-    bank would not fit a sensible host buffer); stage times come from the library's event diagnostics."""
-    import ctypes
-    import numpy as np
-    import evavos_b200 as ev
-    from evavos_b200 import _lib
-    ck, cv, t, h, w, k, seed, desc = cfg
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    hw, n_pos, n_banks = h * w, t * h * w, 2
-    banks, queries = [], []
-    g = torch.Generator(device=dev).manual_seed(seed + rank)
-    for b in range(n_banks):
-        bank = ev.MemoryBank(k, ck, cv, h, w, t, dev, value_dtype=torch.bfloat16, keep_reference_layout=False)
-        for f in range(t):
-            kf = torch.randn(1, ck, h, w, generator=g, device=dev).to(torch.bfloat16).float()
-            vf = torch.randn(k, cv, 1, h, w, generator=g, device=dev).to(torch.bfloat16).float()
-            bank.append(kf, vf)
-        banks.append(bank)
-        queries.append(torch.randn(1, ck, h, w, generator=g, device=dev).to(torch.bfloat16).float())
-    prob = torch.rand(k, 1, h * 16, w * 16, device=dev)
-    stream = torch.cuda.current_stream(dev)
-
-    def step(i):
-        out, _ = ev.memory_read(banks[i % n_banks], queries[i % n_banks], TOP_K)
-        return out, ev.aggregate_wbg(prob, keep_bg=True)
-
-    for i in range(args.warmup):
-        step(i)
-    torch.cuda.synchronize(dev)
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record(stream)
-    for i in range(args.steps):
-        step(i)
-    t1.record(stream)
-    torch.cuda.synchronize(dev)
-    elapsed_ms = t0.elapsed_time(t1)
-    lib = _lib.load()
-    lib.evavos_stage_timing(1)
-    acc = np.zeros(4)
-    for i in range(5):
-        step(i)
-        ms = (ctypes.c_float * 4)()
-        lib.evavos_stage_timing_read(ms)
-        acc += np.array(list(ms)) / 5
-    lib.evavos_stage_timing(0)
-    if rank != 0:
-        return
-    flops = 2.0 * n_pos * hw * ck + 2.0 * k * cv * TOP_K * hw
-    bytes_alg = 2.0 * (n_pos * ck + hw * ck + k * cv * min(n_pos, TOP_K * hw)) + 4.0 * k * cv * hw
-    t_roof = max(flops / 1390.2e12, bytes_alg / (peaks()[0] * 1e9))
-    line = {
-        "metric": "memory-read query-frames/sec", "value": world * args.steps / (elapsed_ms * 1e-3), "unit": "query-frames/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": args.workload + ": " + desc, "top_k": TOP_K, "memory_positions": n_pos, "queries_per_frame": hw,
-                   "objects": k, "l2": f"{n_banks} rotating banks of {2 * k * cv * n_pos / 1e9:.1f} GB"},
-        "gpu_launches": KERNELS_PER_STEP * args.steps,
-        "stages_us": {"filter": acc[0] * 1e3, "exact_fallback": acc[1] * 1e3, "finalize": acc[2] * 1e3, "readout": acc[3] * 1e3},
-        "roofline": {"bound": "balanced (SURVEY 8d: 308 us tensor vs 333 us HBM)", "achieved": None, "peak": None,
-                     "unit": "fraction of max(F_alg / P_tc, B_alg / BW_hbm)", "frac": t_roof / (elapsed_ms / args.steps * 1e-3),
-                     "traffic": None, "t_roof_us": t_roof * 1e6},
-        "cpu_baseline": {"value": None, "unit": "query-frames/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": "skipped: the dense fp32 affinity of this config is 13.3 GB (x3 temporaries)"},
-    }
-    print(json.dumps(line), flush=True)
-
-
+# ----------------------------------------------------------------------------------------------- cfg3 (end to end)
 def run_cfg3(args, cfg, rank, world, local_rank):
     """BASELINE.json configs[2]: end-to-end InferenceCore.interact on independent synthetic 480p videos, one process
     per GPU, no collective.  A step is one video (mask on frame 0, propagated to the other 31 frames); the conv
@@ -350,11 +502,10 @@ def run_cfg3(args, cfg, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------- the headline arm
 def run_ours(args, cfg, rank, world, local_rank):
     import evavos_b200 as ev
-    from evavos_b200 import _lib
     from evavos_b200.host_api import memory_read_host
-    import ctypes
 
     ck, cv, t, h, w, k, seed, desc = cfg
     dev = torch.device("cuda", local_rank)
@@ -366,42 +517,35 @@ def run_ours(args, cfg, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
 
     hw, n_pos = h * w, t * h * w
+    pk = peaks()
     # --- resident inputs: N_BANKS distinct banks (rank-specific seeds: independent videos per GPU) ---
-    banks, queries = [], []
-    for b in range(N_BANKS):
-        mk, qk, mv = synth(seed + 100 * b + 10007 * rank, ck, cv, t, h, w, k)
-        bank = ev.MemoryBank(k, ck, cv, h, w, t, dev, keep_reference_layout=False)
-        for f in range(t):  # built the way do_pass builds it: one append per memory frame
-            bank.append(mk[:, :, f].to(dev), mv[:, :, f:f + 1].to(dev))
-        banks.append(bank)
-        queries.append(qk.to(dev))
+    banks, queries = build_banks(cfg, dev, N_BANKS, seed_shift=10007 * rank)
+    q1 = [q[:, :, 0].contiguous() for q in queries]
     prob = torch.rand(k, 1, h * 16, w * 16, device=dev)
-    idx = torch.empty((hw, TOP_K), dtype=torch.int32, device=dev)
-    wgt = torch.empty((hw, TOP_K), dtype=torch.float32, device=dev)
-    lib = _lib.load()
     stream = torch.cuda.current_stream(dev)
+    outs = [torch.empty((k, cv, h, w), dtype=torch.float32, device=dev) for _ in range(2)]
+    outs5 = [torch.empty((k, cv, MEM_FREQ, h, w), dtype=torch.float32, device=dev) for _ in range(2)]
 
-    ro_events = []
+    def read(i):
+        return ev.memory_read(banks[i % N_BANKS], q1[i % N_BANKS], TOP_K, out=outs[i % 2])
 
-    def step(i, timed):
-        bank, qk = banks[i % N_BANKS], queries[i % N_BANKS]
-        # fused read, split at the readout only to bracket the dominant kernel with events
-        _, aff = ev.memory_read(bank, qk, TOP_K, want_readout=False, want_topk=True)
-        out = torch.empty((k, cv, hw), dtype=torch.float32, device=dev)
-        sh = bank.shadow()
-        if timed:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-        _lib.check(lib.evavos_readout(ctypes.byref(sh), aff.idx.data_ptr(), aff.weight.data_ptr(), hw, TOP_K,
-                                      out.data_ptr(), 0, 0, stream.cuda_stream))
-        if timed:
-            e1.record(stream)
-            ro_events.append((e0, e1))
-        agg = ev.aggregate_wbg(prob, keep_bg=True)
-        return out, agg
+    def agg(i):
+        return ev.aggregate_wbg(prob, keep_bg=True)
+
+    def step(i):
+        read(i)
+        return agg(i)
+
+    def read5(i):
+        return ev.memory_read(banks[i % N_BANKS], queries[i % N_BANKS], TOP_K, out=outs5[i % 2])
+
+    def step5(i):
+        read5(i)
+        for _ in range(MEM_FREQ):
+            agg(i)
 
     for i in range(args.warmup):
-        step(i, False)
+        step(i)
     torch.cuda.synchronize(dev)
     if dist:
         dist.barrier()
@@ -412,20 +556,29 @@ def run_ours(args, cfg, rank, world, local_rank):
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record(stream)
     for i in range(args.steps):
-        step(i, True)
+        step(i)
     t1.record(stream)
     torch.cuda.synchronize(dev)
     if dist:
         dist.barrier()
     elapsed_ms = t0.elapsed_time(t1)
     clocks = sampler.stop() if rank == 0 else None
-    ro_ms = sum(a.elapsed_time(b) for a, b in ro_events) / len(ro_events)
+    ms5 = time_loop(step5, max(3, args.steps // MEM_FREQ), 2, stream, dev)
     if dist:
-        tm = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        tm = torch.tensor([elapsed_ms, ms5], device=dev, dtype=torch.float64)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(tm.item())
+        elapsed_ms, ms5 = float(tm[0].item()), float(tm[1].item())
+    steps5 = max(3, args.steps // MEM_FREQ)
 
-    # --- e2e: host buffers through the host-buffer C-ABI entry point, fewer steps (PCIe-bound) ---
+    # --- instrumented pass over the same steps: per-kernel times; distinct value rows of a step ---
+    stages = stage_pass(read, agg, args.steps, stream, dev)
+    stages5 = stage_pass(read5, None, steps5, stream, dev)
+    _, aff = ev.memory_read(banks[0], q1[0], TOP_K, want_readout=False, want_topk=True)
+    distinct = int(torch.unique(aff.idx).numel())
+    _, aff5 = ev.memory_read(banks[0], queries[0], TOP_K, want_readout=False, want_topk=True)
+    distinct5 = int(torch.unique(aff5.idx).numel())
+
+    # --- e2e: host buffers; streaming (bank persists) and stateless (evavos_memread_host) ---
     mk, qk, mv = synth(seed + 10007 * rank, ck, cv, t, h, w, k)
     h_mk = mk.reshape(ck, n_pos).contiguous().pin_memory()
     h_qk = qk.reshape(ck, hw).contiguous().pin_memory()
@@ -434,9 +587,6 @@ def run_ours(args, cfg, rank, world, local_rank):
     h_prob = prob.cpu().pin_memory()
     h_agg = torch.empty((k + 1, 1, h * 16, w * 16), dtype=torch.float32).pin_memory()
     e2e_steps = max(3, min(args.steps, 20))
-
-    # streaming e2e: the bank persists; per step H2D = query (+ 1/mem_freq of a new memory frame) + probabilities
-    mem_freq = 5
     s_bank = ev.MemoryBank(k, ck, cv, h, w, t, dev)              # reference-layout tensors + shadow, like do_pass
     s_bank.write_frames(0, mk.to(dev), mv.to(dev))
     h_q = [torch.randn(1, ck, h, w, generator=torch.Generator().manual_seed(seed + 7 * j)).pin_memory() for j in range(4)]
@@ -446,15 +596,15 @@ def run_ours(args, cfg, rank, world, local_rank):
 
     def stream_step(i):
         q = h_q[i % 4].to(dev, non_blocking=True)
-        if i % mem_freq == 0:
-            s_bank.write_frames((i // mem_freq) % t, h_newk.to(dev, non_blocking=True), h_newv.to(dev, non_blocking=True))
+        if i % MEM_FREQ == 0:    # a new memory frame every mem_freq-th step, rewritten in place in a rotating slot
+            s_bank.write_frames((i // MEM_FREQ) % t, h_newk.to(dev, non_blocking=True), h_newv.to(dev, non_blocking=True))
         out, _ = ev.memory_read(s_bank, q, TOP_K)
-        agg = ev.aggregate_wbg(h_prob.to(dev, non_blocking=True), keep_bg=True)
+        a = ev.aggregate_wbg(h_prob.to(dev, non_blocking=True), keep_bg=True)
         h_out.copy_(out.view(k, cv, hw), non_blocking=True)
-        h_agg.copy_(agg, non_blocking=True)
+        h_agg.copy_(a, non_blocking=True)
         torch.cuda.synchronize(dev)
 
-    s_h2d = h_q[0].numel() * 4 + (h_newk.numel() + h_newv.numel()) * 4 // mem_freq + h_prob.numel() * 4
+    s_h2d = h_q[0].numel() * 4 + (h_newk.numel() + h_newv.numel()) * 4 // MEM_FREQ + h_prob.numel() * 4
     s_d2h = h_out.numel() * 4 + h_agg.numel() * 4
     for i in range(5):
         stream_step(i)
@@ -466,10 +616,6 @@ def run_ours(args, cfg, rank, world, local_rank):
         stream_step(i)
     torch.cuda.synchronize(dev)
     stream_s = time.perf_counter() - c0
-    if dist:
-        tm = torch.tensor([stream_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        stream_s = float(tm.item())
 
     def e2e_step():
         h2d, d2h = memory_read_host(h_mk, h_qk, h_mv, TOP_K, out=h_out)
@@ -489,20 +635,37 @@ def run_ours(args, cfg, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - c0
     if dist:
-        tm = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        tm = torch.tensor([stream_s, e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        e2e_s = float(tm.item())
+        stream_s, e2e_s = float(tm[0].item()), float(tm[1].item())
         dist.barrier()
+
+    # --- the reference's own torch sequence on this GPU (rank 0's number is reported) ---
+    gb = gpu_baseline(cfg, (mk.to(dev), qk.to(dev), mv.to(dev)), max(3, min(args.steps, 10)), dev, stream)
+    del s_bank
+    torch.cuda.empty_cache()
+
+    # --- N > 1: the memory-axis sharded long-video read (BASELINE.json configs[3]) over the same process group ---
+    sharded = None
+    if world > 1:
+        sharded = run_sharded(args, WORKLOADS["cfg4"], rank, world, local_rank, dist=dist, emit=False)
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
 
+    step_us = 1e3 * elapsed_ms / args.steps
+    shape = (ck, cv, n_pos, hw, k, h * 16 * w * 16)
+    dom, kernels, step_roof = rooflines(shape, stages, step_us, distinct, 4, pk)
+    dom5, kernels5, step_roof5 = rooflines(shape, dict(stages5), 1e3 * ms5 / steps5, distinct5, 4, pk, frames=MEM_FREQ)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        traffic = tr.get(args.workload, {}).get(dom["kernel"])
+        dom["traffic_source"] = tr.get("source")
+    except Exception:
+        pass
     value = world * args.steps / (elapsed_ms * 1e-3)
-    peak, peak_src = peaks()
-    # readout kernel, per launch: every needed value row once + output once + (idx, weight) once
-    ro_bytes = 4 * k * cv * min(n_pos, TOP_K * hw) + 4 * k * cv * hw + 8 * TOP_K * hw
-    achieved = ro_bytes / (ro_ms * 1e-3) / 1e9
     line = {
         "metric": "memory-read query-frames/sec", "value": value, "unit": "query-frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -510,34 +673,44 @@ def run_ours(args, cfg, rank, world, local_rank):
         "config": {"workload": args.workload + ": " + desc, "top_k": TOP_K, "CK": ck, "CV": cv, "memory_positions": n_pos,
                    "queries_per_frame": hw, "objects": k,
                    "l2": f"{N_BANKS} rotating banks, {N_BANKS * (4 * k * cv * n_pos + 4 * ck * n_pos) / 1e6:.0f} MB of inputs > 126 MB L2",
-                   "filter": "tcgen05 bf16 candidate filter + exact fp32 rescoring", "parallelism": f"independent videos x{world}"},
+                   "filter": "tcgen05 bf16 candidate filter (sampled threshold pass + one candidate sweep) + exact fp32 rescoring",
+                   "parallelism": f"independent videos x{world}"},
         "clocks": clocks,
         "e2e": {"value": world * s_steps / stream_s, "unit": "query-frames/s", "h2d_bytes_per_step": int(s_h2d),
                 "d2h_bytes_per_step": int(s_d2h), "steps": s_steps,
                 "note": "public API, pinned host buffers, synchronised every step: H2D query key + decoder probabilities + "
-                        "(every 5th step) one new memory frame appended in place; D2H readout + aggregated probabilities; "
-                        "the bank itself is engine state, as in the reference.  (A two-frames-in-flight variant with the "
-                        "copies on their own streams was measured slower on this platform: 484 vs 1047 qf/s.)"},
+                        "(every 5th step) one new memory frame rewritten in place; D2H readout + aggregated probabilities; "
+                        "the bank itself is engine state, as in the reference"},
         "e2e_full_upload": {"value": world * e2e_steps / e2e_s, "unit": "query-frames/s", "h2d_bytes_per_step": int(h2d_b),
                             "d2h_bytes_per_step": int(d2h_b), "steps": e2e_steps,
                             "note": "evavos_memread_host: stateless, the whole bank + query H2D, shadow build, read, D2H, every step"},
         "gpu_launches": KERNELS_PER_STEP * args.steps,
-        "roofline": {"bound": "hbm", "kernel": "readout_f32_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "us_per_launch": ro_ms * 1e3, "algorithmic_bytes": ro_bytes,
-                     "share_of_step": ro_ms / (elapsed_ms / args.steps)},
+        "stages_us": stages,
+        "roofline": dict(dom, traffic=traffic, peak_source=pk["source"], kernels=kernels, step=step_roof,
+                         share_of_step=dom["us_per_launch"] / sum(v["us_per_launch"] for v in kernels.values()),
+                         note="dominant = longest kernel of the step; kernel times from the instrumented pass (events "
+                              "between kernels defeat PDL overlap: they add up to more than ms_per_step)"),
+        "batched_read": {"value": world * MEM_FREQ * steps5 / (ms5 * 1e-3), "unit": "query-frames/s",
+                         "query_frames_per_launch": MEM_FREQ, "ms_per_launch": ms5 / steps5, "steps": steps5,
+                         "stages_us": stages5,
+                         "roofline": {"dominant": dom5["kernel"], "kernels": kernels5, "step": step_roof5},
+                         "note": "the read the product issues (inference_core.py): the mem_freq query frames between two "
+                                 "memory appends in ONE launch + their 5 aggregations"},
+        "gpu_baseline": dict(gb, speedup=value / world / gb["value"]),
+        "parity_note": "GPU tests (-m gpu) hold the gates: top-k sets vs the fp64 oracle, readout rel-L2, goldens of the live "
+                       "reference; e2e goldens are 6-7 frames at <=120x150 with random weights and cuDNN TF32 off",
     }
-    traffic_file = os.path.join(ROOT, "profiles", "readout_traffic.json")
-    if os.path.exists(traffic_file):
-        try:
-            line["roofline"]["traffic"] = json.load(open(traffic_file)).get(args.workload)
-        except Exception:
-            pass
     if world == 1:
-        cpu_steps = 3
-        rate, info = cpu_reference_rate(cfg, cpu_steps, 1, budget_s=30.0)
+        rate, info = cpu_reference_rate(cfg, 3, 1, budget_s=30.0)
         line["cpu_baseline"] = {"value": rate, "unit": "query-frames/s", "cores": info["cores"], "kind": "port",
                                 "sample": info["sample"]}
+        for name in ("cfg4", "cfg5"):
+            try:
+                line[name] = side_workload(name, args, dev, stream, pk)
+            except Exception as e:
+                line[name] = {"error": repr(e)[:300]}
+    if sharded is not None:
+        line["sharded_cfg4"] = sharded
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
@@ -560,10 +733,14 @@ def main():
         run_reference(args, cfg, rank, world)
     elif args.workload == "cfg4":
         run_sharded(args, cfg, rank, world, local_rank)
-    elif args.workload == "cfg5":
-        run_cfg5(args, cfg, rank, world, local_rank)
     elif args.workload == "cfg3":
         run_cfg3(args, cfg, rank, world, local_rank)
+    elif args.workload == "cfg5":
+        dev = torch.device("cuda", local_rank)
+        torch.cuda.set_device(dev)
+        if rank == 0:
+            res = side_workload("cfg5", args, dev, torch.cuda.current_stream(dev), peaks())
+            print(json.dumps(res), flush=True)
     else:
         run_ours(args, cfg, rank, world, local_rank)
 

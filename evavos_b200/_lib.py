@@ -41,7 +41,7 @@ class MemReadArgs(ctypes.Structure):
         ("topk_score", _c_vp), ("workspace", _c_vp),
         ("workspace_bytes", _c_i64), ("n_pos", _c_i64), ("n_query", _c_i64), ("query_ch_stride", _c_i64),
         ("readout_obj_stride", _c_i64), ("readout_ch_stride", _c_i64),
-        ("top_k", _c_i32), ("path", _c_i32), ("n_sm", _c_i32), ("reserved", _c_i32),
+        ("top_k", _c_i32), ("path", _c_i32), ("n_sm", _c_i32), ("sample_stride", _c_i32),
     ]
 
 

@@ -40,10 +40,13 @@ def attention_readout(mem_key: torch.Tensor, query_key: torch.Tensor, vec: torch
     out = torch.empty((n_vec, n_query), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        need = lib.evavos_attention_workspace_bytes(n_vec, n_mem, n_query, n_sm)
-        ws = _workspace.get(dev, max(int(need), 1))
-        _lib.check(lib.evavos_attention_readout(mk.data_ptr(), mk.stride(0), qk.data_ptr(), qk.stride(0),
-                                                vec.data_ptr(), vec.stride(0), n_vec, ck, n_mem, n_query,
-                                                out.data_ptr(), out.stride(0), ws.data_ptr(), ws.numel(), n_sm,
-                                                _lib.current_stream_ptr(dev)))
+        # the kernel carries at most 32 mask rows per query: more objects (> 15) take several launches
+        for r0 in range(0, n_vec, 32):
+            rows = min(32, n_vec - r0)
+            need = lib.evavos_attention_workspace_bytes(rows, n_mem, n_query, n_sm)
+            ws = _workspace.get(dev, max(int(need), 1))
+            _lib.check(lib.evavos_attention_readout(mk.data_ptr(), mk.stride(0), qk.data_ptr(), qk.stride(0),
+                                                    vec[r0:].data_ptr(), vec.stride(0), rows, ck, n_mem, n_query,
+                                                    out[r0:].data_ptr(), out.stride(0), ws.data_ptr(), ws.numel(), n_sm,
+                                                    _lib.current_stream_ptr(dev)))
     return out

@@ -1,4 +1,5 @@
 // extern "C" entry points of libevavos_sm100.so (see include/evavos.h for the contract).
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -23,20 +24,24 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 namespace {
 
+// SM count of the CURRENT device, cached per device ordinal (a process may drive several GPUs).
 int device_sm_count(int* n_sm) {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0;
-    EVAVOS_CUDA_OK(cudaGetDevice(&dev));
+  constexpr int kMaxDev = 64;
+  static std::atomic<int> cached[kMaxDev];
+  int dev = 0;
+  EVAVOS_CUDA_OK(cudaGetDevice(&dev));
+  int have = (dev >= 0 && dev < kMaxDev) ? cached[dev].load(std::memory_order_relaxed) : 0;
+  if (have == 0) {
     int major = 0;
     EVAVOS_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     if (major != 10) {
       set_error("libevavos_sm100 needs an sm_100 (B200) device, found compute capability major %d", major);
       return EVAVOS_ERR_UNSUPPORTED;
     }
-    EVAVOS_CUDA_OK(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev));
+    EVAVOS_CUDA_OK(cudaDeviceGetAttribute(&have, cudaDevAttrMultiProcessorCount, dev));
+    if (dev >= 0 && dev < kMaxDev) cached[dev].store(have, std::memory_order_relaxed);
   }
-  *n_sm = cached;
+  *n_sm = have;
   return EVAVOS_OK;
 }
 
@@ -55,7 +60,7 @@ struct Carve {
 };
 
 // Lays the workspace out; with base == nullptr only the size is computed.
-Carve carve_workspace(const EvavosMemReadArgs& a, int n_chunks, uint8_t* base) {
+Carve carve_workspace(const EvavosMemReadArgs& a, int n_chunks, int n_sm, uint8_t* base) {
   Carve c;
   memset(&c, 0, sizeof(c));
   const int64_t mt = ceil_div(a.n_query, 128);
@@ -69,8 +74,8 @@ Carve carve_workspace(const EvavosMemReadArgs& a, int n_chunks, uint8_t* base) {
   c.sb.class_max = reinterpret_cast<float*>(take(n_chunks > 0 ? sizeof(float) * (size_t)n_chunks * nq_pad * 128 : 0));
   c.sb.tau = reinterpret_cast<float*>(take(sizeof(float) * nq_pad));
   c.sb.cand_cnt = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * nq_pad));
-  c.sb.cand = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * nq_pad * kCandCap));
-  c.sb.pending = take(n_chunks > 0 ? score_pass_pending_bytes(a.n_query, n_chunks) : 0);
+  c.sb.cand = reinterpret_cast<int2*>(take(sizeof(int2) * nq_pad * kCandCap));
+  c.sb.strip = take(n_chunks > 0 ? score_pass_strip_bytes(a.n_query, n_chunks, n_sm) : 0);
   c.sb.grid_counter = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * (size_t)mt));
   c.idx = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * a.n_query * a.top_k));
   c.weight = reinterpret_cast<float*>(take(sizeof(float) * a.n_query * a.top_k));
@@ -170,32 +175,55 @@ size_t evavos_memread_workspace_bytes(const EvavosMemReadArgs* args) {
   if (args->n_sm > 0) n_sm = args->n_sm;
   else if (device_sm_count(&n_sm)) n_sm = 148;
   const int chunks = use_tensor_path(*args) ? score_pass_chunks(args->n_pos, args->n_query, n_sm) : 0;
-  return carve_workspace(*args, chunks, nullptr).total;
+  return carve_workspace(*args, chunks, n_sm, nullptr).total;
 }
 
 // ---- optional per-stage timing of evavos_memread (diagnostics; CUDA events on the caller's stream) ----------
+// A ring of event sets, one per evavos_memread call, so that a timed loop needs no synchronisation between calls;
+// evavos_stage_timing_read waits for the newest set and averages every set recorded since the last read.
 namespace {
+constexpr int kTimingRing = 256;
 bool g_timing = false;
-cudaEvent_t g_ev[5];
+cudaEvent_t g_ev[kTimingRing][5];
 bool g_ev_made = false;
+int g_ev_next = 0;    // set the next call records into
+int g_ev_count = 0;   // sets recorded since the last read (<= kTimingRing)
 inline void stage_mark(int i, cudaStream_t st) {
-  if (g_timing) cudaEventRecord(g_ev[i], st);
+  if (g_timing) cudaEventRecord(g_ev[g_ev_next][i], st);
+}
+inline void stage_done() {
+  if (!g_timing) return;
+  g_ev_next = (g_ev_next + 1) % kTimingRing;
+  if (g_ev_count < kTimingRing) ++g_ev_count;
 }
 }  // namespace
 
 int evavos_stage_timing(int32_t enable) {
   if (enable && !g_ev_made) {
-    for (int i = 0; i < 5; ++i) EVAVOS_CUDA_OK(cudaEventCreate(&g_ev[i]));
+    for (int r = 0; r < kTimingRing; ++r)
+      for (int i = 0; i < 5; ++i) EVAVOS_CUDA_OK(cudaEventCreate(&g_ev[r][i]));
     g_ev_made = true;
   }
   g_timing = enable != 0;
+  g_ev_count = 0;
   return EVAVOS_OK;
 }
 
 int evavos_stage_timing_read(float* ms4) {
-  if (!g_ev_made || !ms4) { set_error("stage timing not enabled"); return EVAVOS_ERR_INVALID; }
-  EVAVOS_CUDA_OK(cudaEventSynchronize(g_ev[4]));
-  for (int i = 0; i < 4; ++i) EVAVOS_CUDA_OK(cudaEventElapsedTime(&ms4[i], g_ev[i], g_ev[i + 1]));
+  if (!g_ev_made || !ms4 || g_ev_count == 0) { set_error("stage timing: nothing recorded"); return EVAVOS_ERR_INVALID; }
+  const int newest = (g_ev_next + kTimingRing - 1) % kTimingRing;
+  EVAVOS_CUDA_OK(cudaEventSynchronize(g_ev[newest][4]));
+  double acc[4] = {0, 0, 0, 0};
+  for (int c = 0; c < g_ev_count; ++c) {
+    const int r = (g_ev_next + kTimingRing - 1 - c) % kTimingRing;
+    for (int i = 0; i < 4; ++i) {
+      float ms = 0.f;
+      EVAVOS_CUDA_OK(cudaEventElapsedTime(&ms, g_ev[r][i], g_ev[r][i + 1]));
+      acc[i] += ms;
+    }
+  }
+  for (int i = 0; i < 4; ++i) ms4[i] = (float)(acc[i] / g_ev_count);
+  g_ev_count = 0;
   return EVAVOS_OK;
 }
 
@@ -210,12 +238,12 @@ int evavos_memread(const EvavosMemReadArgs* a, evavos_stream_t stream) {
   const int chunks = tensor ? score_pass_chunks(a->n_pos, a->n_query, n_sm) : 0;
   if (!a->workspace) { set_error("workspace is NULL"); return EVAVOS_ERR_WORKSPACE; }
   uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(a->workspace), 1024));
-  const Carve probe = carve_workspace(*a, chunks, nullptr);
+  const Carve probe = carve_workspace(*a, chunks, n_sm, nullptr);
   if ((int64_t)probe.total > a->workspace_bytes) {
     set_error("workspace too small: need %zu bytes, got %lld", probe.total, (long long)a->workspace_bytes);
     return EVAVOS_ERR_WORKSPACE;
   }
-  const Carve c = carve_workspace(*a, chunks, base);
+  const Carve c = carve_workspace(*a, chunks, n_sm, base);
   const int CK = a->bank.CK;
 
   int32_t* idx = a->topk_idx ? a->topk_idx : c.idx;
@@ -224,26 +252,22 @@ int evavos_memread(const EvavosMemReadArgs* a, evavos_stream_t stream) {
   // 1. candidate generation (the query is consumed in the caller's layout; no query shadow)
   stage_mark(0, st);
   if (tensor) {
+    const int stride = score_pass_sample_stride(a->n_pos, a->sample_stride);
     rc = launch_score_select(a->query, a->query_ch_stride, a->bank.key_tiles, a->bank.key_maxnorm, a->n_pos, a->n_query,
-                             a->top_k, chunks, n_sm, c.sb.class_max, c.sb.tau, c.sb.cand, c.sb.cand_cnt, c.sb.pending,
-                             c.sb.grid_counter, st);
-    if (rc) return rc;
-    stage_mark(1, st);
-    // queries whose candidate list overflowed (massive ties) are redone exactly; a no-op launch otherwise
-    rc = launch_brute_select(a->bank.key_pm, a->query, a->query_ch_stride, CK, a->n_pos, a->n_query, a->top_k, 1,
-                             c.sb.cand, c.sb.cand_cnt, n_sm, st);
-    if (rc) return rc;
+                             a->top_k, chunks, stride, n_sm, c.sb.class_max, c.sb.tau, c.sb.cand, c.sb.cand_cnt,
+                             c.sb.strip, c.sb.grid_counter, st);
   } else {
-    stage_mark(1, st);
-    rc = launch_brute_select(a->bank.key_pm, a->query, a->query_ch_stride, CK, a->n_pos, a->n_query, a->top_k, 0,
+    rc = launch_brute_select(a->bank.key_pm, a->query, a->query_ch_stride, CK, a->n_pos, a->n_query, a->top_k,
                              c.sb.cand, c.sb.cand_cnt, n_sm, st);
-    if (rc) return rc;
   }
+  if (rc) return rc;
+  stage_mark(1, st);   // (stage 1, the round-1 exact fallback launch, no longer exists: always ~0)
   stage_mark(2, st);
 
-  // 2. exact rescoring, top-k, softmax
-  rc = launch_finalize(a->bank.key_pm, a->query, a->query_ch_stride, CK, a->n_query, a->top_k, c.sb.cand,
-                       c.sb.cand_cnt, nullptr, idx, weight, a->topk_score, st);
+  // 2. tightening of the list (tensor path), exact rescoring, top-k, softmax; a query whose list overflowed
+  //    (massive ties) is redone exactly inside the same kernel
+  rc = launch_finalize(a->bank.key_pm, a->query, a->query_ch_stride, CK, a->n_pos, a->n_query, a->top_k, c.sb.cand,
+                       c.sb.cand_cnt, tensor ? 1 : 0, a->bank.key_maxnorm, idx, weight, a->topk_score, st);
   if (rc) return rc;
   stage_mark(3, st);
 
@@ -254,6 +278,7 @@ int evavos_memread(const EvavosMemReadArgs* a, evavos_stream_t stream) {
     if (rc) return rc;
   }
   stage_mark(4, st);
+  stage_done();
   return EVAVOS_OK;
 }
 
@@ -353,15 +378,21 @@ namespace {
 struct HostScratch {
   uint8_t* dev = nullptr;
   size_t bytes = 0;
+  int device = -1;   // ordinal the scratch was allocated on
 };
-HostScratch g_scratch;
+HostScratch g_scratch;   // evavos_memread_host is synchronous and documented as not re-entrant
 }  // namespace
 
 int evavos_release_host_scratch(void) {
   if (g_scratch.dev) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (g_scratch.device >= 0 && g_scratch.device != cur) cudaSetDevice(g_scratch.device);
     cudaFree(g_scratch.dev);
+    if (g_scratch.device >= 0 && g_scratch.device != cur) cudaSetDevice(cur);
     g_scratch.dev = nullptr;
     g_scratch.bytes = 0;
+    g_scratch.device = -1;
   }
   return EVAVOS_OK;
 }
@@ -408,10 +439,13 @@ int evavos_memread_host(const float* mem_key, const float* query, const float* m
   const size_t o_kpm = take(b_key), o_tiles = take(evavos_key_tiles_bytes(n_pos)), o_max = take(4);
   const size_t o_vpm = take(b_val), o_ws = take(ws);
   const size_t total = off + 1024;
-  if (g_scratch.bytes < total) {
+  int cur_dev = 0;
+  EVAVOS_CUDA_OK(cudaGetDevice(&cur_dev));
+  if (g_scratch.bytes < total || g_scratch.device != cur_dev) {
     evavos_release_host_scratch();
     EVAVOS_CUDA_OK(cudaMalloc(&g_scratch.dev, total));
     g_scratch.bytes = total;
+    g_scratch.device = cur_dev;
   }
   uint8_t* d = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(g_scratch.dev), 1024));
   cudaStream_t st = 0;

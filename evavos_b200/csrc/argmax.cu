@@ -2,7 +2,7 @@
 //
 // InferenceCore.interact ends with one torch.argmax launch per frame, a strided un-padding slice and a D2H copy
 // (mivos/inference_core.py:247-257).  Here every padded pixel of every frame is read once: the channel argmax
-// (first maximal channel, like torch.argmax) goes to `masks` (T, nh, nw) and, for pixels inside the original
+// (first maximal channel, NaN counting as the largest value, like torch.argmax) goes to `masks` (T, nh, nw) and, for pixels inside the original
 // frame, to the contiguous un-padded `out` (T, h, w) that is copied to the host.  HBM-bound:
 // algorithmic bytes = C * T * nh * nw * 4 read + T * (nh * nw + h * w) written.
 #include "common.cuh"
@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(256) argmax_unpad_kernel(const float* __restri
       }
 #pragma unroll
       for (int j = 0; j < VEC; ++j)
-        if (cur[j] > best[j]) { best[j] = cur[j]; arg[j] = (uint8_t)c; }
+        // torch.argmax orders NaN above everything and keeps the first one
+        if (cur[j] > best[j] || (cur[j] != cur[j] && best[j] == best[j])) { best[j] = cur[j]; arg[j] = (uint8_t)c; }
     }
     if (masks) {
       if constexpr (VEC == 4) *reinterpret_cast<uchar4*>(masks + e0) = make_uchar4(arg[0], arg[1], arg[2], arg[3]);

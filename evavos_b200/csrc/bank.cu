@@ -94,21 +94,9 @@ __global__ void __launch_bounds__(256) write_keys_kernel(
     }
   }
 
-  // Rows between the end of the written range and the end of its tile become empty rows.
-  if (tiles != nullptr && blk0 + nb == n_pos) {
-    const int64_t end = pos0 + n_pos;
-    const int r_end = (int)(end % kTilePos);
-    if (r_end != 0) {
-      uint8_t* tb = tiles + (end / kTilePos) * (int64_t)kTileBytes;
-      for (int e = tid; e < (kTilePos - r_end) * 8; e += 256) {
-        const int r = r_end + e / 8, chunk = e % 8;
-        *reinterpret_cast<uint4*>(tb + swizzle128_offset(r, chunk)) = make_uint4(0, 0, 0, 0);
-        if (chunk < 2)
-          *reinterpret_cast<uint4*>(tb + kTileKeyBytes + swizzle32_offset(r, chunk)) =
-              chunk == 0 ? nh_slice(kEmptyNh) : make_uint4(0, 0, 0, 0);
-      }
-    }
-  }
+  // Rows of a tile beyond the written range are NOT touched: a frame may be rewritten in the middle of a bank
+  // (MemoryBank.write_frames accepts any slot), and the filter masks columns >= n_pos itself, so stale or
+  // never-written rows of the last tile can not reach a candidate list.
 
   if (maxnorm != nullptr) {
     float nrm = (i < nb) ? sqrtf(ss) : 0.f;

@@ -14,7 +14,8 @@ constexpr int kTilePos = EVAVOS_TILE_POS;        // 128 positions per key tile i
 constexpr int kTileKeyBytes = 128 * 128;         // 128 rows x 128 B (64 bf16)
 constexpr int kTileBytes = EVAVOS_TILE_BYTES;    // + 128 rows x 32 B: bf16 (hi, mid, lo) split of -|k|^2/2, zero padded
 constexpr float kEmptyNh = -1.0e30f;             // "-|k|^2/2" of an empty row: can never pass a threshold
-constexpr int kCandCap = 256;                    // candidate slots per query handed to the finalizer
+constexpr int kCandCap = 1024;                   // (position, filter score) candidate slots per query handed to the finalizer
+constexpr int kMaxSurvivors = 256;               // candidates that may survive the finalizer's own bound and get rescored
 
 // ---- error plumbing (thread-local message behind evavos_last_error) -------------------------
 void set_error(const char* fmt, ...);
@@ -88,6 +89,14 @@ __device__ __forceinline__ float affinity_from_parts(float kk, float kq, float q
   return t * inv_sqrt_ck;
 }
 
+// Error bound of the bf16 filter score S' = q^.k^ - |k|^2/2 against its exact value:
+// |q^.k^ - q.k| <= 2^-8 (1 + 2^-10) |q||k| for bf16 round-to-nearest operands, plus slack for the tensor-core fp32
+// accumulation and the rounding of -|k|^2/2.  The filter and the finalizer both subtract 2 eps from their bounds.
+__device__ __forceinline__ float filter_eps(float q_norm, float key_maxnorm) {
+  const float qn = q_norm * 1.0001f;
+  return 0.004f * qn * key_maxnorm + 2.0e-6f * key_maxnorm * key_maxnorm + 1.0e-30f;
+}
+
 // ---- launchers implemented in the .cu files -------------------------------------------------
 int launch_write_keys(const EvavosBankShadow& b, const float* src, int64_t src_ch_stride, int64_t pos0,
                       int64_t n_pos, float* dst_ref, int64_t dst_ref_ch_stride, cudaStream_t st);
@@ -99,24 +108,26 @@ struct SelectBuffers {
   float* class_max;   // [G][MT*128][128]
   float* tau;         // [nq_pad]
   int32_t* cand_cnt;  // [nq_pad]
-  int32_t* cand;      // [nq_pad][kCandCap]
-  void* pending;      // sweep-2 staging strips (score_pass_pending_bytes)
+  int2* cand;         // [nq_pad][kCandCap] (position, filter score bits; the exact SIMT selection leaves the score 0)
+  void* strip;        // phase-B staging strips of the filter's epilogue threads (score_pass_strip_bytes)
   unsigned int* grid_counter;
 };
 
 // The query is always addressed in the caller's layout: element (c, q) at query[c * query_ch_stride + q].
-// only_overflow != 0: process only queries whose candidate count exceeded kCandCap (tcgen05 filter overflow).
 int launch_brute_select(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_pos,
-                        int64_t n_query, int top_k, int only_overflow, int32_t* cand, int32_t* cand_cnt, int n_sm,
-                        cudaStream_t st);
-int launch_finalize(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_query,
-                    int top_k, const int32_t* cand, const int32_t* cand_cnt, const int32_t* only_flag, int32_t* out_idx,
-                    float* out_weight, float* out_score, cudaStream_t st);
+                        int64_t n_query, int top_k, int2* cand, int32_t* cand_cnt, int n_sm, cudaStream_t st);
+// scored != 0: the entries carry filter scores (tcgen05 path) and the list is first cut down with the bound the
+// scores themselves give; key_maxnorm is only read then.
+int launch_finalize(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_pos,
+                    int64_t n_query, int top_k, const int2* cand, const int32_t* cand_cnt, int scored,
+                    const float* key_maxnorm, int32_t* out_idx, float* out_weight, float* out_score, cudaStream_t st);
 int launch_score_select(const float* query, int64_t query_ch_stride, const void* key_tiles, const float* key_maxnorm,
-                        int64_t n_pos, int64_t n_query, int top_k, int n_chunks, int n_sm, float* class_max, float* tau,
-                        int32_t* cand, int32_t* cand_cnt, void* pending, unsigned int* grid_counter, cudaStream_t st);
-size_t score_pass_pending_bytes(int64_t n_query, int n_chunks);
+                        int64_t n_pos, int64_t n_query, int top_k, int n_chunks, int sample_stride, int n_sm,
+                        float* class_max, float* tau, int2* cand, int32_t* cand_cnt, void* strip,
+                        unsigned int* grid_counter, cudaStream_t st);
+size_t score_pass_strip_bytes(int64_t n_query, int n_chunks, int n_sm);
 int score_pass_chunks(int64_t n_pos, int64_t n_query, int n_sm);
+int score_pass_sample_stride(int64_t n_pos, int requested);
 
 int launch_readout(const EvavosBankShadow& b, const int32_t* idx, const float* weight, int64_t n_query,
                    int top_k, float* out, int64_t out_obj_stride, int64_t out_ch_stride, cudaStream_t st);

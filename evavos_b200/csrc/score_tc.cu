@@ -4,43 +4,47 @@
 // (2 S' - |q|^2)/sqrt(CK), a per-query monotone map, prop_net.py:86-90).  The -|k|^2/2 term is
 // part of the contraction: every key row carries a 16-wide extra K slice (hi, mid, lo bf16 split
 // of -|k|^2/2, zeros) that meets (1, 1, 1, 0...) on the query side, so the accumulator tile IS the
-// score tile and the epilogue spends one instruction per score.  The THW x HW matrix never leaves
-// the SM: each 128x128 accumulator tile is consumed out of TMEM and only O(k) numbers per query
-// reach HBM.
+// score tile.  The THW x HW matrix never leaves the SM: each 128x128 accumulator tile is consumed
+// out of TMEM and only O(k) numbers per query reach HBM.
 //
-//   sweep 1: running maximum of S' per (query, column class n mod 128) -> class_max.
-//            The k-th largest of a query's 128 class maxima is a lower bound on its k-th best
-//            score (k distinct positions reach it); the CTAs agree on it across the grid.
-//   sweep 2: same contraction; every position with S' >= tau_q (bound minus a rigorous bf16
-//            error margin) is appended to the query's candidate list, which therefore
-//            contains the exact fp32 top-k.  finalize_kernel's exact rescoring picks it.
-// Both sweeps run inside ONE cooperative launch (score_select_kernel): the TMA and MMA warps simply stream the
-// chunk's tiles twice and run ahead into sweep 2 while the epilogue warps exchange thresholds.
-// (Running the exact finalizer inside this kernel as well was measured slower: a CTA finalizes its dozen queries
-// in sequence, while the separate finalize_kernel runs all queries at once.)
+//   phase A (threshold pass): every R-th key tile of the chunk (R = sample_stride) is contracted and the
+//            epilogue keeps a running maximum of S' per (query, column class) -> class_max.  The k-th largest
+//            of a query's 128 class maxima is a lower bound on its k-th best score over the SAMPLE, hence over
+//            the whole bank (k distinct positions reach it); the CTAs of a query tile agree on it across the grid.
+//   phase B (candidate pass): ALL key tiles; every position with S' >= tau_q (bound minus a rigorous bf16
+//            error margin) is appended with its score to the query's candidate list, which therefore contains
+//            the exact fp32 top-k.  The finalizer tightens the list with the k-th largest S' it finds in it
+//            (a bound that needs no second look at the bank) and rescoring the survivors exactly picks the top-k.
+// R = 1 is the round-1 algorithm (two full sweeps); R = 2..4 contracts 1.5..1.25 sweeps at the price of
+// ~1.26 k R candidates per query instead of ~1.26 k.
+// Both phases run inside ONE cooperative launch (score_select_kernel): the TMA and MMA warps stream
+// n_sample + n_tiles tiles and run ahead into phase B while the epilogue warps exchange thresholds.
 //
 // Roles per CTA (640 threads, 1 CTA/SM, one wave): warp 0 = TMA producers (4 lanes issuing cp.async.bulk of
-// pre-swizzled 20 KB key tile images; one issuing thread keeps a single copy in flight, ~50 B/clk),
-// warps 1-2 = MMA issuers (one elected lane each, alternating tiles, 5 x tcgen05.mma 128x128x16 per tile),
-// warp 3 = TMEM allocator, warps 4-19 = epilogue (four warpgroups, each thread owns one query row and 32
-// accumulator columns; branch-free inner loops).  Rings: 6 shared-memory key stages, 4 TMEM
-// accumulator stages (4 x 128 columns = all 512).  The query tile is converted to bf16 and
-// swizzled into shared memory by the CTA itself.
+// pre-swizzled 20 KB key tile images into an 8-stage ring), warp 1 = the MMA issuer (one elected lane, every tile
+// in order, 5 x tcgen05.mma 128x128x16 per tile with the query operand in TMEM), warp 3 = TMEM allocator,
+// warps 4-19 = epilogue: two groups of 8 warps that serve alternate tiles, each thread one query row and 64
+// accumulator columns as two 32-column tcgen05.ld.  3 TMEM accumulator stages (3 x 128 columns); the query
+// operand occupies columns [384, 424).
 #include "common.cuh"
 
 namespace evavos {
 
 #ifdef EVAVOS_TRACE
 // Timeline of CTA 0 (clock64): rows = producer issue, MMA waits done, MMA issued, epilogue acc_full seen,
-// epilogue TMEM load done, epilogue math done; columns = tile index (first 64 tiles).
+// epilogue TMEM load done, epilogue math done; columns = iteration index minus g_trace_i0 (a 64-iteration window).
 __device__ long long g_trace[6][64];
-#define EVAVOS_TR(row, i) do { if (blockIdx.x == 0 && (i) < 64) g_trace[row][i] = clock64(); } while (0)
+__device__ int g_trace_i0 = 0;
+#define EVAVOS_TR(row, i) do { const int _ti = (i) - g_trace_i0; if (blockIdx.x == 0 && _ti >= 0 && _ti < 64) g_trace[row][_ti] = clock64(); } while (0)
+#define EVAVOS_TR_MARK(slot) do { if (blockIdx.x == 0) g_trace[0][slot] = clock64(); } while (0)
 #else
 #define EVAVOS_TR(row, i) do { } while (0)
+#define EVAVOS_TR_MARK(slot) do { } while (0)
 #endif
 
 // Compile-time timing experiments (-DEVAVOS_EXP=bits; results are wrong while a bit is set):
-// 1 = the epilogue skips the TMEM load, 2 = skips its math.
+// 1 = the epilogue skips the TMEM load, 2 = skips its math, 4 = the producers copy only 4 KB of every tile image
+// (is the L2 -> shared-memory path the bound?), 8 = phase B never takes the hit path (cost of staging).
 #ifndef EVAVOS_EXP
 #define EVAVOS_EXP 0
 #endif
@@ -50,34 +54,16 @@ namespace {
 constexpr int kStages = 8;
 constexpr int kAccStages = 3;   // 3 x 128 accumulator columns; the query operand lives in columns [384, 424)
 constexpr int kQueryCol = 384;
-// Epilogue organisation (EVAVOS_GROUPS):
-//   1: 16 warps visit every tile in lock-step, 32 accumulator columns each; two MMA issuer warps.
-//   2: two groups of 8 warps serve even / odd tiles, 64 columns per warp as 2 x 32; one in-order MMA issuer.
-//   3: three groups of 8 warps, group g owns accumulator stage g (iterations i = g mod 3), 64 columns per warp as
-//      4 x 16 so that a thread fits in 72 registers and 28 warps are resident; one in-order MMA issuer.
-#ifndef EVAVOS_RARE
-#define EVAVOS_RARE (-1)   // -1: decide per launch from the bank size; 0 / 1: force (timing experiments)
-#endif
-#ifndef EVAVOS_GROUPS
-#define EVAVOS_GROUPS 2
-#endif
-constexpr int kNumGroups = EVAVOS_GROUPS;
-constexpr int kEpiWarps = kNumGroups == 3 ? 24 : 16;
+constexpr int kEpiWarps = 16;   // two groups of 8 warps on alternate iterations
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kThreads = 128 + kEpiThreads;
 constexpr int kProducers = 4;   // TMA-issuing lanes of warp 0 (kStages % kProducers == 0)
-constexpr int kCols = kNumGroups == 3 ? 16 : 32;   // accumulator columns per tcgen05.ld and epilogue thread
-constexpr int kClasses = kNumGroups == 3 ? 96 : 128;   // column classes per query and chunk (sweep 1)
-// Scores per staged hit group (sweep 2 tests one maximum per group).  Measured, filter time in us for 4 | 8:
-// cfg2 (32 k positions, a hit in 23 % | 40 % of the warp-groups) 43.8 | 52.7, cfg4 (324 k positions) 168.8 | 162.9.
-#ifndef EVAVOS_GROUP
-#define EVAVOS_GROUP 4
-#endif
-constexpr int kGroup = EVAVOS_GROUP;
-constexpr int kPend = 8 + kCols / kGroup;  // staged hit groups per epilogue thread (flushed when more than 8 wait)
-constexpr bool kSplit = kNumGroups > 1;   // epilogue warp groups on different tiles (see the epilogue)
+constexpr int kCols = 32;       // accumulator columns per tcgen05.ld
+constexpr int kClasses = 128;   // column classes per query and chunk (phase A)
+constexpr int kStrip = 16;      // staged 8-score groups per epilogue thread before they are resolved into the list
 constexpr int kBarBytes = 256;
 constexpr int kSmemBytes = kTileBytes * kStages + kBarBytes + 1024;
+constexpr uint32_t kCopyBytes = (EVAVOS_EXP & 4) ? 4096 : kTileBytes;   // bytes the producers move per tile image
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -168,20 +154,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
-  if constexpr (kCols == 16) tmem_ld16(taddr, v);
-  else tmem_ld32(taddr, v);
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct PassParams {
@@ -194,72 +166,44 @@ struct PassParams {
   int n_mtiles;
   int n_ktiles;
   int n_chunks;
+  int sample_stride;    // R: phase A contracts every R-th tile of the chunk
   float* class_max;
   float* tau;
-  int32_t* cand;
+  int2* cand;           // [nq_pad][kCandCap] (position, score bits)
   int32_t* cand_cnt;
-  float4* pend_score;   // [grid][kPend * kGroup / 4][kEpiThreads] scores of staged hit groups (sweep 2)
-  int32_t* pend_pos;    // [grid][kPend][kEpiThreads] first position of each staged group
+  float4* strip_score;  // [grid][2 * kStrip][kEpiThreads] scores of the staged 8-column groups (phase B)
+  int32_t* strip_pos;   // [grid][kStrip][kEpiThreads] first position of each staged group
   const float* key_maxnorm;
   unsigned int* grid_counter;  // one counter per query tile of the launch, zeroed before every launch
   int m_tile0;          // first query tile of this launch
   int top_k;
-  int rare_hits;        // sweep 2 tests a whole block before its groups (see the epilogue)
+  int flush_period;     // phase-B visits between two synchronised strip resolutions
 };
 
-// Sweep 2 stages every group of kGroup adjacent scores whose maximum reaches the threshold (scores + first
-// position) in a private strip of the workspace; the strip is resolved into the query's candidate list out of
-// line.  Hits are rare: about top_k + margin per query over the whole bank.
-__device__ __noinline__ void flush_pending(const float4* ps, const int32_t* pp, int n, float thr, int32_t* cand,
-                                           int32_t* cand_cnt, int64_t q) {
-  int hits = 0;
-  for (int e = 0; e < n * (kGroup / 4); ++e) {
-    const float4 s = ps[e * kEpiThreads];
-    hits += (s.x >= thr) + (s.y >= thr) + (s.z >= thr) + (s.w >= thr);
-  }
+// Phase B stages every group of 8 adjacent scores whose maximum reaches the threshold (scores + first position) in
+// a private strip of the workspace - plain stores, nothing to wait for - and counts the group's hits.  The strip is
+// resolved into the query's candidate list out of line: one atomic reserves `hits` slots, one pass copies the hits.
+// Entries beyond kCandCap are dropped, the count keeps growing and the finalizer falls back to its exact path for
+// that query.
+//
+// WHEN a strip is resolved matters more than how: a resolving warp is away for thousands of cycles (dependent L2
+// round trips), its group cannot release the next accumulator stage without it, and the MMA pipeline stalls behind
+// the slowest of the group's 8 warps.  With every thread resolving whenever ITS strip filled up, some warp of a
+// group was almost always away (measured: 2 060 clk per tile at cfg5).  So all threads resolve TOGETHER, every
+// flush_period visits (sized by the host so that a strip holds a few groups by then): one short stall per period
+// with all lanes busy instead of a stall per tile.  A strip that fills up earlier is still resolved at once (rare).
+__device__ __noinline__ void flush_strip(const float4* ss, const int32_t* sp, int n, int hits, float thr, int2* cand,
+                                         int32_t* cand_cnt, int64_t q) {
   int at = atomicAdd(cand_cnt + q, hits);
-  for (int e = 0; e < n * (kGroup / 4); ++e) {
-    const float4 s = ps[e * kEpiThreads];
-    const int32_t n0 = pp[(e / (kGroup / 4)) * kEpiThreads] + 4 * (e % (kGroup / 4));
-    const float v[4] = {s.x, s.y, s.z, s.w};
+  for (int e = 0; e < n; ++e) {
+    const float4 s0 = ss[(int64_t)(2 * e) * kEpiThreads], s1 = ss[(int64_t)(2 * e + 1) * kEpiThreads];
+    const int32_t n0 = sp[(int64_t)e * kEpiThreads];
+    const float v[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 8; ++k) {
       if (v[k] >= thr) {
-        if (at < kCandCap) cand[q * kCandCap + at] = n0 + k;
+        if (at < kCandCap) cand[q * kCandCap + at] = make_int2(n0 + k, __float_as_int(v[k]));
         ++at;
-      }
-    }
-  }
-}
-
-// 32 accumulator columns of one query row, held as registers.
-template <int PASS, bool PARTIAL>
-__device__ __forceinline__ void consume_tile(const float* v, float* cmax, float thr, int32_t n_first, int valid,
-                                             float4* ps, int32_t* pp, int& pending) {
-  // valid: number of in-range columns among this thread's kCols (only read when PARTIAL)
-  if constexpr (PASS == 1) {
-    // kCols / 2 classes per call, two columns each: one 3-input max per two scores
-#pragma unroll
-    for (int j = 0; j < kCols / 2; ++j) {
-      const float s0 = (PARTIAL && j >= valid) ? kEmptyNh : v[j];
-      const float s1 = (PARTIAL && j + kCols / 2 >= valid) ? kEmptyNh : v[j + kCols / 2];
-      cmax[j] = fmaxf(fmaxf(cmax[j], s0), s1);
-    }
-  } else {
-#pragma unroll
-    for (int g = 0; g < kCols / kGroup; ++g) {
-      float sg[kGroup];
-#pragma unroll
-      for (int e = 0; e < kGroup; ++e) sg[e] = (PARTIAL && g * kGroup + e >= valid) ? -INFINITY : v[g * kGroup + e];
-      float m = sg[0];
-#pragma unroll
-      for (int e = 1; e < kGroup; ++e) m = fmaxf(m, sg[e]);
-      if (m >= thr) {
-#pragma unroll
-        for (int h = 0; h < kGroup / 4; ++h)
-          ps[(pending * (kGroup / 4) + h) * kEpiThreads] = make_float4(sg[4 * h], sg[4 * h + 1], sg[4 * h + 2], sg[4 * h + 3]);
-        pp[pending * kEpiThreads] = n_first + g * kGroup;
-        ++pending;
       }
     }
   }
@@ -340,19 +284,21 @@ __device__ __forceinline__ void warp_threshold(const PassParams& p, int64_t q, i
   for (int t = 1; t < 4; ++t) sel = ((kth & 3) == t) ? v[t] : sel;
   const float kth_value = __shfl_sync(0xffffffffu, sel, kth >> 2);
   if (lane == 0) {
-    const float qn = sqrtf(qsq) * 1.0001f;
-    const float kn = *p.key_maxnorm;
-    // |q^.k^ - q.k| <= 2^-8 (1 + 2^-10) |q||k| for bf16 round-to-nearest operands, plus slack for the
-    // tensor-core fp32 accumulation and the rounding of -|k|^2/2.
-    const float eps = 0.004f * qn * kn + 2.0e-6f * kn * kn + 1.0e-30f;
-    p.tau[q] = kth_value - 2.0f * eps;
+    p.tau[q] = kth_value - 2.0f * filter_eps(sqrtf(qsq), *p.key_maxnorm);
     p.cand_cnt[q] = 0;
   }
 }
 
-// One persistent CTA per (query tile, memory chunk).  The producer and MMA warps stream the chunk's key tiles
-// twice; the epilogue warps take running class maxima on the first sweep, agree on per-query thresholds across
-// the grid, and collect candidates on the second sweep.
+// max of 8 scores: 3 three-input maxima and one two-input
+__device__ __forceinline__ float max8(const float* v) {
+  const float a = fmaxf(fmaxf(v[0], v[1]), v[2]);
+  const float b = fmaxf(fmaxf(v[3], v[4]), v[5]);
+  return fmaxf(fmaxf(fmaxf(v[6], v[7]), a), b);
+}
+
+// One persistent CTA per (query tile, memory chunk).  The producer and MMA warps stream the chunk's sample tiles
+// and then all its tiles; the epilogue warps take running class maxima over the sample, agree on per-query
+// thresholds across the grid, and collect scored candidates over all tiles.
 __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -368,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(base_ptr + kTileBytes * kStages + 16 * kStages + 16 * kAccStages);
 
-  if (threadIdx.x == 0) EVAVOS_TR(0, 56);
+  if (threadIdx.x == 0) EVAVOS_TR_MARK(56);
   // warp index through a shuffle: the compiler then knows it is warp-uniform, keeps everything derived from it
   // (loop counters, stage addresses, UMMA descriptors) in uniform registers and issues the five tcgen05.mma of a
   // tile back to back instead of wrapping each in an R2UR broadcast loop (~95 -> ~40 clk of issue per MMA)
@@ -378,8 +324,10 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
   const int t0 = (int)(((int64_t)chunk * p.n_ktiles) / p.n_chunks);
   const int t1 = (int)(((int64_t)(chunk + 1) * p.n_ktiles) / p.n_chunks);
   const int n_tiles = t1 - t0;
-  const int n_iter = 2 * n_tiles;  // every key tile is contracted twice
-  auto tile_of = [&](int i) { return t0 + (i >= n_tiles ? i - n_tiles : i); };
+  const int R = p.sample_stride;
+  const int n_sample = (n_tiles + R - 1) / R;     // phase A: tiles t0, t0 + R, t0 + 2R, ...
+  const int n_iter = n_sample + n_tiles;          // phase B: every tile of the chunk
+  auto tile_of = [&](int i) { return i < n_sample ? t0 + i * R : t0 + (i - n_sample); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -388,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
     }
     for (int a = 0; a < kAccStages; ++a) {
       mbar_init(bar_acc_full + 8 * a, 1);
-      mbar_init(bar_acc_empty + 8 * a, kSplit ? 8 : kEpiWarps);   // warps that visit one tile
+      mbar_init(bar_acc_empty + 8 * a, 8);   // the 8 warps of the group that visits the tile
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -401,8 +349,8 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
   if (threadIdx.x == 0) {
     const int pre = n_iter < kStages ? n_iter : kStages;
     for (int i = 0; i < pre; ++i) {
-      mbar_arrive_expect_tx(bar_full + 8 * i, kTileBytes);
-      bulk_g2s(stage0 + i * kTileBytes, p.key_tiles + (int64_t)tile_of(i) * kTileBytes, kTileBytes, bar_full + 8 * i);
+      mbar_arrive_expect_tx(bar_full + 8 * i, kCopyBytes);
+      bulk_g2s(stage0 + i * kTileBytes, p.key_tiles + (int64_t)tile_of(i) * kTileBytes, kCopyBytes, bar_full + 8 * i);
     }
   }
   tc_fence_before();
@@ -438,8 +386,12 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (threadIdx.x == 0) EVAVOS_TR(0, 57);
+  if (threadIdx.x == 0) EVAVOS_TR_MARK(57);
 
+  // Register budget: 640 threads x 96 at launch.  The producer / issuer warpgroup needs few registers and hands
+  // its surplus to the four epilogue warpgroups, whose phase-B loop holds 64 accumulator values per thread.
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
   if (warp == 0) {
     // ===== TMA producers: kProducers lanes, lane l streams iterations i = l (mod kProducers) =====
     // (one thread keeps only one bulk copy in flight; several lanes keep several)
@@ -450,22 +402,19 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
         const uint32_t ph = (uint32_t)((i / kStages) & 1);
         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
         EVAVOS_TR(0, i);
-        mbar_arrive_expect_tx(bar_full + 8 * s, kTileBytes);
-        bulk_g2s(stage0 + s * kTileBytes, p.key_tiles + (int64_t)tile_of(i) * kTileBytes, kTileBytes, bar_full + 8 * s);
+        mbar_arrive_expect_tx(bar_full + 8 * s, kCopyBytes);
+        bulk_g2s(stage0 + s * kTileBytes, p.key_tiles + (int64_t)tile_of(i) * kTileBytes, kCopyBytes, bar_full + 8 * s);
       }
     }
-  } else if (warp == 1 || warp == 2) {
-    // ===== MMA issuers: warp 1 takes the even iterations, warp 2 the odd ones =====
-    // (measured: one thread spends ~350 clk per tile in its two barrier waits; two threads overlap them with the
-    //  other's MMAs: 830 -> 600 clk per tile.  Three threads, or one thread interleaving two tiles, were slower.
-    //  Each commit tracks the MMAs of its own thread, which is exactly one tile.)
+  } else if (warp == 1) {
+    // ===== MMA issuer: ONE elected lane, every iteration in order =====
+    // The epilogue groups see an accumulator stage only at every other use, and an mbarrier parity wait is only
+    // sound for a waiter that cannot fall two phases behind: with two issuers tile i + 1 may complete before tile
+    // i, a group runs ahead onto a stage whose previous phase it never observed, takes the stale parity for
+    // "ready" and the pipeline deadlocks (seen on B200 in round 1; tests/test_pipeline_protocol.py models it).
+    // In-order commits from a single thread rule that out.
     const uint32_t a_tmem = tmem_base + kQueryCol;
-    // kSplit: ONE issuer, every iteration in order.  The epilogue groups then see an accumulator stage only at every
-    // other use, and an mbarrier parity wait is only sound for a waiter that cannot fall two phases behind: with
-    // two issuers tile i + 1 may complete before tile i, a group runs ahead onto a stage whose previous phase it
-    // never observed, takes the stale parity for "ready" and the pipeline deadlocks (seen on B200).  In-order
-    // commits from a single thread rule that out.
-    for (int i = kSplit ? (warp == 1 ? 0 : n_iter) : warp - 1; i < n_iter; i += kSplit ? 1 : 2) {
+    for (int i = 0; i < n_iter; ++i) {
       const int s = i % kStages, a = i % kAccStages;
       mbar_wait(bar_full + 8 * s, (uint32_t)((i / kStages) & 1));
       mbar_wait(bar_acc_empty + 8 * a, (uint32_t)(((i / kAccStages) & 1) ^ 1));
@@ -486,147 +435,173 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
       }
       __syncwarp();
     }
-  } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> running class max (sweep 1) / staged hit groups (sweep 2) =====
-    // kSplit: the 16 warps form two groups of 8 that serve alternate tiles (even / odd tile index), each warp 64
-    // accumulator columns as two 32-column loads, so that one group's math overlaps the other group's loads and
-    // the MMAs of the next tile.  Otherwise all 16 warps visit every tile in lock-step, 32 columns each.
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    // ===== epilogue: TMEM -> registers -> running class max (phase A) / staged candidates (phase B) =====
+    // The 16 warps form two groups of 8 that serve alternate iterations, each warp 64 accumulator columns as two
+    // 32-column loads, so that one group's math overlaps the other group's loads and the MMAs of the next tile.
     const int ew = warp - 4;
     const int quarter = ew & 3;           // TMEM lane quarter this warp may access
-    const int grp = kSplit ? (ew >> 3) : 0;
-    const int colbase = kSplit ? ((ew >> 2) & 1) * 64 : (ew >> 2) * kCols;
-    constexpr int kBlocks = kSplit ? 64 / kCols : 1;   // tcgen05.ld blocks per visited tile
+    const int grp = ew >> 3;
+    const int colbase = ((ew >> 2) & 1) * 64;
     const int row = quarter * 32 + lane;
     const int et = threadIdx.x - 128;
     const int64_t q = (int64_t)m_tile * 128 + row;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    // iterations this warp visits: 2 groups - tiles of the group's parity; 3 groups - i = grp (mod 3), i.e. always
-    // accumulator stage `grp`, in both sweeps; lock-step - all
-    constexpr int i_step = kSplit ? kNumGroups : 1;
-    const int i_first = kNumGroups == 3 ? grp : (kNumGroups == 2 ? ((((t0 & 1) == grp) ? 0 : 1)) : 0);
-    const int i_first2 = kNumGroups == 3 ? n_tiles + (grp + 3 - n_tiles % 3) % 3 : n_tiles + i_first;
 
-    // visit(i, math): wait for accumulator tile i, read this warp's columns block by block (the stage goes back to
-    // the MMA warps as soon as the last block is in registers) and call math(block, values, first position).
+    // visit(i, math): wait for accumulator tile i, read this warp's 64 columns as two 32-column blocks (the stage
+    // goes back to the MMA warp as soon as the second block is in registers) and call
+    // math(block, values, first position, number of valid columns).
     auto visit = [&](int i, auto&& math) {
       const int a = i % kAccStages;
       mbar_wait(bar_acc_full + 8 * a, (uint32_t)((i / kAccStages) & 1));
       tc_fence_after();
       if (threadIdx.x == 128) EVAVOS_TR(3, i);
+      const int64_t n_first = (int64_t)tile_of(i) * kTilePos + colbase;
 #pragma unroll
-      for (int blk = 0; blk < kBlocks; ++blk) {
+      for (int blk = 0; blk < 2; ++blk) {
         float v[kCols];
         if constexpr (!(EVAVOS_EXP & 1)) {
-          tmem_ld_cols(lane_addr + (uint32_t)(a * 128 + colbase + blk * kCols), v);
+          tmem_ld32(lane_addr + (uint32_t)(a * 128 + colbase + blk * kCols), v);
           tmem_ld_wait();
         } else {
+#pragma unroll
           for (int j = 0; j < kCols; ++j) v[j] = kEmptyNh;
         }
-        if (blk == kBlocks - 1) {
+        if (blk == 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acc_empty + 8 * a);  // registers hold the tile: release the TMEM stage
           if (threadIdx.x == 128) EVAVOS_TR(4, i);
         }
-        math(blk, v, (int64_t)tile_of(i) * kTilePos + colbase + blk * kCols);
+        const int64_t n0 = n_first + blk * kCols;
+        if constexpr (!(EVAVOS_EXP & 2)) {
+          const int64_t left = p.n_pos - n0;
+          if (left < kCols) {   // rows of the bank's last tile at or beyond n_pos hold no position (warp-uniform)
+#pragma unroll
+            for (int j = 0; j < kCols; ++j) v[j] = (j < left) ? v[j] : -INFINITY;
+          }
+          math(blk, v, n0);
+        }
       }
       if (threadIdx.x == 128) EVAVOS_TR(5, i);
     };
 
-    // ---- sweep 1: class maxima ----
+    // ---- phase A: class maxima over the sample tiles ----
     {
-      // Column classes per thread: 16 x (columns j and j + 16 of a 32-column block), one set per block (kSplit: of
-      // the tiles of this group's parity) or per tile parity (lock-step) - 128 per query and chunk either way.  Any
-      // partition of the positions into classes gives a valid bound; this one costs one FMNMX3 per two scores.
-      constexpr int kOwn = 32;   // class maxima held per thread
-      float cmax[kOwn];
+      // 16 classes per 32-column block (columns j and j + 16 share a class: one 3-input max per two scores),
+      // one set per block -> 32 per thread, 128 per query and chunk (2 groups x 2 column halves x 32).
+      // Any partition of positions into classes gives a valid bound.
+      float cmax[32];
 #pragma unroll
-      for (int j = 0; j < kOwn; ++j) cmax[j] = kEmptyNh;
-      auto class_max = [&](float* cm, const float* v, int64_t n0) {
-        int pending = 0;
-        if constexpr ((EVAVOS_EXP & 2) != 0) {
-        } else if (n0 + kCols > p.n_pos) {
-          const int valid = (int)max((int64_t)0, p.n_pos - n0);
-          consume_tile<1, true>(v, cm, 0.f, (int32_t)n0, valid, nullptr, nullptr, pending);
-        } else {
-          consume_tile<1, false>(v, cm, 0.f, (int32_t)n0, kCols, nullptr, nullptr, pending);
-        }
-      };
-      if constexpr (kSplit) {
-        for (int i = i_first; i < n_tiles; i += i_step)
-          visit(i, [&](int blk, const float* v, int64_t n0) { class_max(cmax + blk * (kCols / 2), v, n0); });
-      } else {
-        int i = 0;   // parity of the tile's index in the bank, not in the chunk
-        if (t0 & 1) visit(i++, [&](int, const float* v, int64_t n0) { class_max(cmax + kCols / 2, v, n0); });
-        for (; i < n_tiles; i += 2) {
-          visit(i, [&](int, const float* v, int64_t n0) { class_max(cmax, v, n0); });
-          if (i + 1 < n_tiles) visit(i + 1, [&](int, const float* v, int64_t n0) { class_max(cmax + kCols / 2, v, n0); });
-        }
-      }
-      if constexpr (kNumGroups == 3) {
-        // 6 (group, half) slots of 16 classes: neighbouring classes of a thread are merged pairwise (96 per query)
-        float4* dst = reinterpret_cast<float4*>(p.class_max + ((int64_t)chunk * p.nq_pad + q) * 128 + (ew >> 2) * 16);
+      for (int j = 0; j < 32; ++j) cmax[j] = kEmptyNh;
+      for (int i = grp; i < n_sample; i += 2)
+        visit(i, [&](int blk, const float* v, int64_t) {
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4)
-          dst[j4] = make_float4(fmaxf(cmax[8 * j4], cmax[8 * j4 + 1]), fmaxf(cmax[8 * j4 + 2], cmax[8 * j4 + 3]),
-                                fmaxf(cmax[8 * j4 + 4], cmax[8 * j4 + 5]), fmaxf(cmax[8 * j4 + 6], cmax[8 * j4 + 7]));
-      } else {
-        float4* dst = reinterpret_cast<float4*>(p.class_max + ((int64_t)chunk * p.nq_pad + q) * 128 + (ew >> 2) * 32);
+          for (int j = 0; j < kCols / 2; ++j)
+            cmax[blk * 16 + j] = fmaxf(fmaxf(cmax[blk * 16 + j], v[j]), v[j + kCols / 2]);
+        });
+      float4* dst = reinterpret_cast<float4*>(p.class_max + ((int64_t)chunk * p.nq_pad + q) * 128 + (ew >> 2) * 32);
 #pragma unroll
-        for (int j4 = 0; j4 < kOwn / 4; ++j4)
-          dst[j4] = make_float4(cmax[j4 * 4], cmax[j4 * 4 + 1], cmax[j4 * 4 + 2], cmax[j4 * 4 + 3]);
-      }
+      for (int j4 = 0; j4 < 8; ++j4)
+        dst[j4] = make_float4(cmax[j4 * 4], cmax[j4 * 4 + 1], cmax[j4 * 4 + 2], cmax[j4 * 4 + 3]);
     }
 
     // ---- thresholds: every CTA of a query tile takes a slice of its 128 rows ----
-    if (threadIdx.x == 128) EVAVOS_TR(0, 60);
+    if (threadIdx.x == 128) EVAVOS_TR_MARK(60);
     epilogue_grid_barrier(p.grid_counter + (blockIdx.x % p.n_mtiles), (unsigned)p.n_chunks);
-    if (threadIdx.x == 128) EVAVOS_TR(0, 61);
+    if (threadIdx.x == 128) EVAVOS_TR_MARK(61);
     {
       const int r0 = (chunk * 128) / p.n_chunks, r1 = ((chunk + 1) * 128) / p.n_chunks;
-      for (int r = r0 + ew; r < r1; r += kEpiThreads / 32) {
+      for (int r = r0 + ew; r < r1; r += kEpiWarps) {
         const int64_t qq = (int64_t)m_tile * 128 + r;
         if (qq < p.n_query) warp_threshold(p, qq, lane);
       }
     }
-    if (threadIdx.x == 128) EVAVOS_TR(0, 62);
+    if (threadIdx.x == 128) EVAVOS_TR_MARK(62);
     epilogue_grid_barrier(p.grid_counter + (blockIdx.x % p.n_mtiles), 2u * (unsigned)p.n_chunks);
-    if (threadIdx.x == 128) EVAVOS_TR(0, 63);
+    if (threadIdx.x == 128) EVAVOS_TR_MARK(63);
 
-    // ---- sweep 2: candidates ----
+    // ---- phase B: scored candidates over all tiles ----
     {
       float thr = INFINITY;
       if (q < p.n_query) thr = __ldcg(p.tau + q);
-      float4* ps = p.pend_score + (int64_t)blockIdx.x * (kPend * kGroup / 4) * kEpiThreads + et;
-      int32_t* pp = p.pend_pos + (int64_t)blockIdx.x * kPend * kEpiThreads + et;
-      int pending = 0;
-      float unused[1];
-      for (int i = i_first2; i < n_iter; i += i_step) {
-        visit(i, [&](int, const float* v, int64_t n0) {
-          if constexpr ((EVAVOS_EXP & 2) != 0) {
-          } else if (n0 + kCols > p.n_pos) {
-            const int valid = (int)max((int64_t)0, p.n_pos - n0);
-            consume_tile<2, true>(v, unused, thr, (int32_t)n0, valid, ps, pp, pending);
-          } else {
-            // banks where a hit is rare per block: one maximum over the whole block first, the per-group test only
-            // when it reaches the threshold (the branch is warp-divergent, but most warps skip the block)
-            bool look = true;
-            if (p.rare_hits) {
-              float m = v[0];
+      float4* ss = p.strip_score + (int64_t)blockIdx.x * (2 * kStrip) * kEpiThreads + et;
+      int32_t* sp = p.strip_pos + (int64_t)blockIdx.x * kStrip * kEpiThreads + et;
+      int pending = 0, hits = 0;
+      // Hierarchical test of one 32-column block, one compare per 32 scores on the way that most blocks take:
+      // maxima of the four 8-column groups, then their maximum against the threshold.  Only a warp that holds a hit
+      // looks at the groups; a lane stages each of its groups that holds one (scores + first position).
+      auto block = [&](const float* v, int32_t n0) {
+        float g[4];
 #pragma unroll
-              for (int j = 1; j < kCols; ++j) m = fmaxf(m, v[j]);
-              look = m >= thr;
+        for (int u = 0; u < 4; ++u) g[u] = max8(v + 8 * u);
+        const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+        if constexpr ((EVAVOS_EXP & 8) == 0) {
+          if (__any_sync(0xffffffffu, m >= thr)) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (g[u] >= thr) {
+                if (pending == kStrip) {
+                  flush_strip(ss, sp, pending, hits, thr, p.cand, p.cand_cnt, q);
+                  pending = hits = 0;
+                }
+                ss[(int64_t)(2 * pending) * kEpiThreads] = make_float4(v[8 * u], v[8 * u + 1], v[8 * u + 2], v[8 * u + 3]);
+                ss[(int64_t)(2 * pending + 1) * kEpiThreads] = make_float4(v[8 * u + 4], v[8 * u + 5], v[8 * u + 6], v[8 * u + 7]);
+                sp[(int64_t)pending * kEpiThreads] = n0 + 8 * u;
+                ++pending;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) hits += v[8 * u + e] >= thr ? 1 : 0;
+              }
             }
-            if (look) consume_tile<2, false>(v, unused, thr, (int32_t)n0, kCols, ps, pp, pending);
           }
-          if (pending > kPend - kCols / kGroup) {  // the next block stages at most kCols / kGroup groups
-            flush_pending(ps, pp, pending, thr, p.cand, p.cand_cnt, q);
-            pending = 0;
+        }
+      };
+      const int i_b0 = n_sample + (((n_sample & 1) == grp) ? 0 : 1);
+      int since_flush = 0;
+      for (int i = i_b0; i < n_iter; i += 2) {
+        // Both 32-column blocks are pulled out of TMEM before any math, so the accumulator stage goes back to the
+        // MMA warp at once: a warp that has to stage hits must not hold up its group's release of the stage.
+        const int a = i % kAccStages;
+        mbar_wait(bar_acc_full + 8 * a, (uint32_t)((i / kAccStages) & 1));
+        tc_fence_after();
+        if (threadIdx.x == 128) EVAVOS_TR(3, i);
+        float v0[kCols], v1[kCols];
+        if constexpr (!(EVAVOS_EXP & 1)) {
+          tmem_ld32(lane_addr + (uint32_t)(a * 128 + colbase), v0);
+          tmem_ld32(lane_addr + (uint32_t)(a * 128 + colbase + kCols), v1);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < kCols; ++j) v0[j] = v1[j] = kEmptyNh;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * a);
+        if (threadIdx.x == 128) EVAVOS_TR(4, i);
+        if constexpr (!(EVAVOS_EXP & 2)) {
+          const int64_t n0 = (int64_t)tile_of(i) * kTilePos + colbase;
+          const int64_t left = p.n_pos - n0;
+          if (left < 2 * kCols) {   // the bank's last tile: rows at or beyond n_pos hold no position (warp-uniform)
+#pragma unroll
+            for (int j = 0; j < kCols; ++j) {
+              v0[j] = (j < left) ? v0[j] : -INFINITY;
+              v1[j] = (j + kCols < left) ? v1[j] : -INFINITY;
+            }
           }
-        });
+          block(v0, (int32_t)n0);
+          block(v1, (int32_t)n0 + kCols);
+          if (++since_flush == p.flush_period) {   // every thread of the CTA resolves its strip on the same visit
+            since_flush = 0;
+            if (pending > 0) flush_strip(ss, sp, pending, hits, thr, p.cand, p.cand_cnt, q);
+            pending = hits = 0;
+          }
+        }
+        if (threadIdx.x == 128) EVAVOS_TR(5, i);
       }
-      if (pending > 0) flush_pending(ps, pp, pending, thr, p.cand, p.cand_cnt, q);
-      if (threadIdx.x == 128) EVAVOS_TR(0, 58);
+      if (pending > 0) flush_strip(ss, sp, pending, hits, thr, p.cand, p.cand_cnt, q);
+      if (threadIdx.x == 128) EVAVOS_TR_MARK(58);
     }
   }
 
@@ -636,7 +611,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
   if (warp == 3) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
-  if (threadIdx.x == 96) EVAVOS_TR(0, 59);
+  if (threadIdx.x == 96) EVAVOS_TR_MARK(59);
 }
 
 }  // namespace
@@ -650,25 +625,45 @@ int score_pass_chunks(int64_t n_pos, int64_t n_query, int n_sm) {
   return (int)g;
 }
 
-size_t score_pass_pending_bytes(int64_t n_query, int n_chunks) {
-  return (size_t)ceil_div(n_query, 128) * n_chunks * kPend * kEpiThreads * (kGroup / 4 * sizeof(float4) + sizeof(int32_t));
+// Phase A contracts every R-th tile.  The expected candidate count grows like ~1.26 k R (plus the error margin),
+// and every candidate costs the epilogue a trip off its fast path; the sample must also keep >= ~48 tiles so that
+// 128 classes over it say something.  Measured on B200: R = 2 for long banks.
+int score_pass_sample_stride(int64_t n_pos, int requested) {
+  const int64_t nt = ceil_div(n_pos, kTilePos);
+  int r = requested > 0 ? requested : 2;
+  if (r > 8) r = 8;
+  const int64_t cap = nt / 48;
+  if (r > cap) r = (int)cap;
+  if (r < 1) r = 1;
+  return r;
+}
+
+size_t score_pass_strip_bytes(int64_t n_query, int n_chunks, int n_sm) {
+  const int64_t mt = ceil_div(n_query, 128);
+  const int64_t per_launch = n_chunks > 1 ? mt : (mt < n_sm ? mt : n_sm);
+  return (size_t)per_launch * n_chunks * kStrip * kEpiThreads * (2 * sizeof(float4) + sizeof(int32_t));
 }
 
 #ifdef EVAVOS_TRACE
 extern "C" int evavos_debug_trace(long long* out) {
   return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 6 * 64);
 }
+extern "C" int evavos_debug_trace_base(int i0) { return (int)cudaMemcpyToSymbol(g_trace_i0, &i0, sizeof(int)); }
 #endif
 
 // Candidate generation for all queries: class maxima, thresholds and candidate lists in one cooperative launch
 // per wave of query tiles (one wave whenever n_query <= 128 * n_sm).
 int launch_score_select(const float* query, int64_t query_ch_stride, const void* key_tiles, const float* key_maxnorm,
-                        int64_t n_pos, int64_t n_query, int top_k, int n_chunks, int n_sm, float* class_max, float* tau,
-                        int32_t* cand, int32_t* cand_cnt, void* pending, unsigned int* grid_counter, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+                        int64_t n_pos, int64_t n_query, int top_k, int n_chunks, int sample_stride, int n_sm,
+                        float* class_max, float* tau, int2* cand, int32_t* cand_cnt, void* strip,
+                        unsigned int* grid_counter, cudaStream_t st) {
+  // per device: the opt-in to > 48 KB of dynamic shared memory is a property of the function ON a device
+  static bool attr_set[64] = {};
+  int dev = 0;
+  EVAVOS_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     EVAVOS_CUDA_OK(cudaFuncSetAttribute(score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int mt_total = (int)ceil_div(n_query, 128);
   const int mt_per_launch = n_chunks > 1 ? mt_total : (mt_total < n_sm ? mt_total : n_sm);
@@ -683,21 +678,27 @@ int launch_score_select(const float* query, int64_t query_ch_stride, const void*
     p.nq_pad = (int64_t)mt_total * 128;
     p.n_ktiles = (int)ceil_div(n_pos, kTilePos);
     p.n_chunks = n_chunks;
+    p.sample_stride = sample_stride;
     p.class_max = class_max;
     p.tau = tau;
     p.cand = cand;
     p.cand_cnt = cand_cnt;
+    p.strip_score = reinterpret_cast<float4*>(strip);
+    p.strip_pos = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(strip) +
+                                             (size_t)mt_per_launch * n_chunks * (2 * kStrip) * kEpiThreads * sizeof(float4));
     p.key_maxnorm = key_maxnorm;
     p.grid_counter = grid_counter;
     p.m_tile0 = m0;
     p.top_k = top_k;
-    // expected candidates per query ~ 1.4 top_k, a block is 32 lanes x kCols scores: rare = a block holds a hit
-    // with probability below ~1/2
-    p.rare_hits = (EVAVOS_RARE >= 0) ? EVAVOS_RARE : ((double)n_pos > 2.0 * 1.4 * top_k * 32.0 * kCols ? 1 : 0);
+    {
+      // expected staged groups per thread and visit: ~1.8 k R candidates per query, a visit covers 64 positions
+      const double per_visit = 1.8 * top_k * sample_stride * 64.0 / (double)n_pos;
+      double period = 3.0 / per_visit;            // ~3 groups per strip (of kStrip = 16) when it is resolved
+      if (period < 4.0) period = 4.0;
+      if (period > 1.0e6) period = 1.0e6;
+      p.flush_period = (int)period;
+    }
     const unsigned grid = (unsigned)(p.n_mtiles * n_chunks);
-    p.pend_score = reinterpret_cast<float4*>(pending);
-    p.pend_pos = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(pending) +
-                                            (size_t)mt_per_launch * n_chunks * (kPend * kGroup / 4) * kEpiThreads * sizeof(float4));
     EVAVOS_CUDA_OK(cudaMemsetAsync(grid_counter, 0, sizeof(unsigned int) * (size_t)p.n_mtiles, st));
     void* args[] = {&p};
     EVAVOS_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(score_select_kernel), dim3(grid),

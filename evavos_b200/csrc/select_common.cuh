@@ -1,16 +1,9 @@
-// Exact fp32 scoring and the per-query finalizer, shared by finalize_kernel and the fused filter kernel.
+// Exact fp32 scoring and the per-query finalizer (one warp per query).
 #pragma once
 
 #include "common.cuh"
 
 namespace evavos {
-
-#ifdef EVAVOS_TRACE
-static __device__ int g_fin_skip = 0;   // timing experiments only: 1 = no row loads, 2 = no rank loop, 4 = no |q|^2 loop
-#define EVAVOS_FIN_SKIP(bit) (g_fin_skip & (bit))
-#else
-#define EVAVOS_FIN_SKIP(bit) 0
-#endif
 
 // kk += |k|^2, kq += k.q over CK channels, channel order 0..CK-1, one FMA per term.
 __device__ __forceinline__ void dot_row(const float4* __restrict__ krow, const float* __restrict__ q, int CK,
@@ -62,7 +55,6 @@ __device__ __forceinline__ float sumsq(const float* __restrict__ q, int CK) {
   return s;
 }
 
-constexpr int kRowChunk = 48;    // candidate key rows staged per round (finalize_query)
 constexpr int kRowStride = 68;   // floats: 16-byte aligned rows, conflict-free LDS.128 when every lane owns a row
 
 // |q|^2 of a 64-channel query held in shared memory, by one converged warp: two channels per lane, butterfly sum.
@@ -75,100 +67,225 @@ __device__ __forceinline__ float sumsq64_warp(const float* q, int lane) {
   return s;
 }
 
-struct FinalizeSmem {
+__device__ __forceinline__ unsigned long long score_key(float s, int32_t n) {
+  // larger = better: score descending, then position ascending
+  return ((unsigned long long)float_to_ordered(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
+}
+
+// Per-warp scratch of the finalizer (one warp finalizes one query).
+struct FinalizeWarpSmem {
   float qs[64];
-  float rows[kRowChunk][kRowStride];
-  unsigned long long keys[kCandCap];
+  float rows[32][kRowStride];
+  unsigned long long keys[kMaxSurvivors];   // survivor positions first, their exact (score, position) keys afterwards
   unsigned long long sel[EVAVOS_MAX_TOPK];
-  float warp_sum[4];
 };
 
-// Finalize one query with a group of 128 threads (tid 0..127; `sync` is the group's barrier).
-// Every thread rescoring one (or two) candidates exactly, keys go to shared memory, each thread ranks its
-// candidates all-pairs (rank = number of candidates with a larger (score, -position) key), and the first top_k
-// ranks are written best-first with their softmax weights exp(s - s0) / sum (prop_net.py:54-57).
-template <typename Sync>
-__device__ __forceinline__ void finalize_query(FinalizeSmem& sm, int tid, int64_t q, const float* __restrict__ key_pm,
-                                               const float* __restrict__ query, int64_t query_ch_stride, int CK,
-                                               int top_k, const int32_t* cand, int cnt_raw,
-                                               int32_t* __restrict__ out_idx, float* __restrict__ out_weight,
-                                               float* __restrict__ out_score, Sync sync) {
-  const int lane = tid & 31, warp = tid >> 5;
-  const int cnt = min(cnt_raw, kCandCap);
-  if (tid < 64) sm.qs[tid] = (tid < CK) ? __ldg(query + (int64_t)tid * query_ch_stride + q) : 0.f;
-  sync();
-  const float inv_sqrt_ck = 1.0f / sqrtf((float)CK);
-  if (CK == 64) {
-    // |q|^2 once per warp (two channels per lane) instead of a 64-step chain in every thread
-    const float qq = sumsq64_warp(sm.qs, lane);
-    // Candidate rows go through shared memory: half a warp fetches one 256-byte row (two full lines per row and
-    // instruction instead of 32 partial ones when every thread walks its own row), then thread t rescoring row t
-    // reads it back with the FMA order of dot_row.
-    for (int base = 0; base < cnt; base += kRowChunk) {
-      const int nrows = min(kRowChunk, cnt - base);
-      if (!EVAVOS_FIN_SKIP(1)) {
-        for (int r = tid >> 4; r < nrows; r += 8) {
-          const int32_t n = __ldcg(cand + q * kCandCap + base + r);
-          const float4 v = __ldg(reinterpret_cast<const float4*>(key_pm + (int64_t)n * 64) + (tid & 15));
-          *reinterpret_cast<float4*>(&sm.rows[r][4 * (tid & 15)]) = v;
-        }
-      }
-      sync();
-      if (tid < nrows) {
-        const int32_t n = __ldcg(cand + q * kCandCap + base + tid);
-        float kk, kq;
-        dot_row_smem64(reinterpret_cast<const float4*>(sm.rows[tid]), sm.qs, kk, kq);
-        const float s = affinity_from_parts(kk, kq, qq, inv_sqrt_ck);
-        sm.keys[base + tid] =
-            ((unsigned long long)float_to_ordered(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
-      }
-      sync();
-    }
-  } else {
-    const float qq = sumsq(sm.qs, CK);
+// A lower bound (20 leading bits) of the k-th largest filter score among list[0..n): radix descent over the
+// order-preserving keys, NJ entries per lane in registers.  n <= 32 * NJ, k <= n.
+template <int NJ>
+__device__ __forceinline__ uint32_t kth_largest_bound(const uint32_t* key, int k) {
+  uint32_t prefix = 0;
+  int need = k;
+  for (int bit = 31; bit >= 12; --bit) {
+    const uint32_t want = (prefix >> bit) | 1u;
+    int c = 0;
 #pragma unroll
-    for (int t = 0; t < kCandCap / 128; ++t) {
-      const int ci = tid + 128 * t;
-      if (ci < cnt) {
-        const int32_t n = __ldcg(cand + q * kCandCap + ci);
+    for (int j = 0; j < NJ; ++j) c += ((key[j] >> bit) == want) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= need) prefix |= 1u << bit;   // the k-th largest has this bit set
+    else need -= c;
+  }
+  return prefix;
+}
+
+// Cut the scored candidate list down to the entries that can still be in the exact top-k and leave their positions
+// in sm.keys[0..ns).  theta = (a lower bound of) the k-th largest filter score in the list: k listed positions reach
+// it, so the k-th best exact score is >= theta - eps and every member of the exact top-k has a filter score
+// >= theta - 2 eps.  Returns ns, or -1 when more than kMaxSurvivors entries survive (massive near-ties).
+template <int NJ>
+__device__ __forceinline__ int prefilter_candidates(FinalizeWarpSmem& sm, const int2* list, int n, int k, float two_eps,
+                                                    int lane) {
+  uint32_t key[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int e = lane + 32 * j;
+    key[j] = e < n ? float_to_ordered(__int_as_float(__ldcg(&list[e].y))) : 0u;
+  }
+  const float theta = ordered_to_float(kth_largest_bound<NJ>(key, k));
+  const uint32_t cut = float_to_ordered(theta - two_eps);
+  int ns = 0;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int e = lane + 32 * j;
+    const bool pass = e < n && key[j] >= cut;
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (pass) {
+      const int slot = ns + __popc(m & ((1u << lane) - 1u));
+      if (slot < kMaxSurvivors) sm.keys[slot] = (unsigned long long)(uint32_t)__ldcg(&list[e].x);
+    }
+    ns += __popc(m);
+  }
+  return ns <= kMaxSurvivors ? ns : -1;
+}
+
+// Exact top-k of one query over ALL positions by one warp: a sorted list in sm.sel, 32 exact scores per step, an
+// insertion only for scores that beat the current k-th (rare once the list has warmed up).  Same (score, position)
+// order as everything else.  This is the slow path of queries whose candidate list overflowed (thousands of
+// tied or nearly tied keys); returns the number of entries (min(top_k, n_pos)).
+__device__ __noinline__ int exact_topk_warp(FinalizeWarpSmem& sm, const float* __restrict__ key_pm, int CK,
+                                            int64_t n_pos, int top_k, float qq, float inv_sqrt_ck, int lane) {
+  int filled = 0;
+  for (int64_t base = 0; base < n_pos; base += 32) {
+    const int64_t n = base + lane;
+    unsigned long long key = 0ull;
+    if (n < n_pos) {
+      float kk, kq;
+      dot_row(reinterpret_cast<const float4*>(key_pm + n * CK), sm.qs, CK, kk, kq);
+      key = score_key(affinity_from_parts(kk, kq, qq, inv_sqrt_ck), (int32_t)n);
+    }
+    unsigned long long kth = filled == top_k ? sm.sel[top_k - 1] : 0ull;
+    unsigned m = __ballot_sync(0xffffffffu, key > kth);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const unsigned long long kk64 = __shfl_sync(0xffffffffu, key, src);
+      kth = filled == top_k ? sm.sel[top_k - 1] : 0ull;
+      if (kk64 <= kth) continue;   // the bar rose while this step's hits were being inserted (warp-uniform)
+      int pos = 0;
+      unsigned long long prev[EVAVOS_MAX_TOPK / 32];
+#pragma unroll
+      for (int g = 0; g < EVAVOS_MAX_TOPK / 32; ++g) {
+        const int i = lane + 32 * g;
+        pos += __popc(__ballot_sync(0xffffffffu, i < filled && sm.sel[i] > kk64));
+        prev[g] = (i >= 1 && i - 1 < filled) ? sm.sel[i - 1] : 0ull;
+      }
+      const int new_filled = min(filled + 1, top_k);
+      __syncwarp();
+#pragma unroll
+      for (int g = 0; g < EVAVOS_MAX_TOPK / 32; ++g) {
+        const int i = lane + 32 * g;
+        if (i == pos) sm.sel[i] = kk64;
+        else if (i > pos && i < new_filled) sm.sel[i] = prev[g];
+      }
+      filled = new_filled;
+      __syncwarp();
+    }
+  }
+  return filled;
+}
+
+// Finalize one query with one warp: cut the candidate list (scored lists only), rescore the survivors exactly,
+// rank them all-pairs (rank = number of survivors with a larger (score, -position) key), and write the first top_k
+// best-first with their softmax weights exp(s - s0) / sum (prop_net.py:54-57).
+__device__ __forceinline__ void finalize_query_warp(FinalizeWarpSmem& sm, int lane, int64_t q,
+                                                    const float* __restrict__ key_pm, const float* __restrict__ query,
+                                                    int64_t query_ch_stride, int CK, int64_t n_pos, int top_k,
+                                                    const int2* __restrict__ cand, int cnt_raw, int scored,
+                                                    const float* __restrict__ key_maxnorm,
+                                                    int32_t* __restrict__ out_idx, float* __restrict__ out_weight,
+                                                    float* __restrict__ out_score) {
+  sm.qs[lane] = (lane < CK) ? __ldg(query + (int64_t)lane * query_ch_stride + q) : 0.f;
+  sm.qs[lane + 32] = (lane + 32 < CK) ? __ldg(query + (int64_t)(lane + 32) * query_ch_stride + q) : 0.f;
+  __syncwarp();
+  const float inv_sqrt_ck = 1.0f / sqrtf((float)CK);
+  const float qq = (CK == 64) ? sumsq64_warp(sm.qs, lane) : sumsq(sm.qs, CK);
+  const int2* list = cand + q * kCandCap;
+
+  int ns = -1;   // survivors in sm.keys, or -1: take the exact path
+  if (cnt_raw <= kCandCap) {
+    if (!scored) {
+      ns = min(cnt_raw, kMaxSurvivors);
+      for (int e = lane; e < ns; e += 32) sm.keys[e] = (unsigned long long)(uint32_t)__ldcg(&list[e].x);
+    } else {
+      const float two_eps = 2.0f * filter_eps(sqrtf(qq), __ldg(key_maxnorm));
+      const int k = min(top_k, cnt_raw);
+      if (cnt_raw <= top_k + 32) {   // a list this short is not worth cutting: rescore all of it
+        ns = cnt_raw;
+        for (int e = lane; e < ns; e += 32) sm.keys[e] = (unsigned long long)(uint32_t)__ldcg(&list[e].x);
+      } else if (cnt_raw <= 256) ns = prefilter_candidates<8>(sm, list, cnt_raw, k, two_eps, lane);
+      else if (cnt_raw <= 512) ns = prefilter_candidates<16>(sm, list, cnt_raw, k, two_eps, lane);
+      else ns = prefilter_candidates<32>(sm, list, cnt_raw, k, two_eps, lane);
+    }
+  }
+  int take;
+  if (ns < 0) {
+    __syncwarp();
+    take = exact_topk_warp(sm, key_pm, CK, n_pos, top_k, qq, inv_sqrt_ck, lane);
+  } else {
+    __syncwarp();
+    // exact rescoring, 32 survivors per round
+    for (int base = 0; base < ns; base += 32) {
+      const int nrows = min(32, ns - base);
+      float s = 0.f;
+      int32_t n = 0;
+      if (CK == 64) {
+        // Rows go through shared memory: half a warp fetches one 256-byte row (two full lines per row and
+        // instruction instead of 32 partial ones when every lane walks its own row), then lane t rescoring row t
+        // reads it back with the FMA order of dot_row.
+        // (all 16 loads of a lane in flight before the first store: the rows come from HBM, one latency per round)
+        float4 buf[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int r = (lane >> 4) + 2 * u;
+          if (r < nrows) {
+            const int32_t nr = (int32_t)(uint32_t)sm.keys[base + r];
+            buf[u] = __ldg(reinterpret_cast<const float4*>(key_pm + (int64_t)nr * 64) + (lane & 15));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int r = (lane >> 4) + 2 * u;
+          if (r < nrows) *reinterpret_cast<float4*>(&sm.rows[r][4 * (lane & 15)]) = buf[u];
+        }
+        __syncwarp();
+        if (lane < nrows) {
+          n = (int32_t)(uint32_t)sm.keys[base + lane];
+          float kk, kq;
+          dot_row_smem64(reinterpret_cast<const float4*>(sm.rows[lane]), sm.qs, kk, kq);
+          s = affinity_from_parts(kk, kq, qq, inv_sqrt_ck);
+        }
+      } else if (lane < nrows) {
+        n = (int32_t)(uint32_t)sm.keys[base + lane];
         float kk, kq;
         dot_row(reinterpret_cast<const float4*>(key_pm + (int64_t)n * CK), sm.qs, CK, kk, kq);
-        const float s = affinity_from_parts(kk, kq, qq, inv_sqrt_ck);
-        sm.keys[ci] = ((unsigned long long)float_to_ordered(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
+        s = affinity_from_parts(kk, kq, qq, inv_sqrt_ck);
       }
+      __syncwarp();
+      if (lane < nrows) sm.keys[base + lane] = score_key(s, n);
     }
-    sync();
-  }
-  const int take = min(top_k, cnt);
-#pragma unroll
-  for (int t = 0; t < kCandCap / 128; ++t) {
-    const int ci = tid + 128 * t;
-    if (ci < cnt) {
-      const unsigned long long mine = sm.keys[ci];
+    __syncwarp();
+    take = min(top_k, ns);
+    for (int c = lane; c < ns; c += 32) {
+      const unsigned long long mine = sm.keys[c];
       int rank = 0;
-      if (EVAVOS_FIN_SKIP(2)) rank = ci;
-      else
-        for (int j = 0; j < cnt; ++j) rank += sm.keys[j] > mine ? 1 : 0;  // broadcast reads; keys are unique
+      for (int j = 0; j < ns; ++j) rank += sm.keys[j] > mine ? 1 : 0;  // broadcast reads; keys are unique
       if (rank < take) sm.sel[rank] = mine;
     }
   }
-  sync();
+  __syncwarp();
   const float s0 = take > 0 ? ordered_to_float((uint32_t)(sm.sel[0] >> 32)) : 0.f;
-  float e = 0.f;
-  if (tid < take) e = expf(ordered_to_float((uint32_t)(sm.sel[tid] >> 32)) - s0);  // exp(values - values[:,0])
-  float part = e;
+  float e[EVAVOS_MAX_TOPK / 32], part[EVAVOS_MAX_TOPK / 32];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-  if (lane == 0) sm.warp_sum[warp] = part;
-  sync();
-  const float total = (sm.warp_sum[0] + sm.warp_sum[1]) + (sm.warp_sum[2] + sm.warp_sum[3]);
-  if (tid < top_k) {
-    const bool live = tid < take;
-    const int64_t o = q * top_k + tid;
-    if (out_idx) out_idx[o] = live ? (int32_t)(0xffffffffu - (uint32_t)(sm.sel[tid] & 0xffffffffull)) : -1;
-    if (out_weight) out_weight[o] = live ? e / total : 0.f;
-    if (out_score) out_score[o] = live ? ordered_to_float((uint32_t)(sm.sel[tid] >> 32)) : -INFINITY;
+  for (int g = 0; g < EVAVOS_MAX_TOPK / 32; ++g) {
+    const int j = lane + 32 * g;
+    e[g] = j < take ? expf(ordered_to_float((uint32_t)(sm.sel[j] >> 32)) - s0) : 0.f;  // exp(values - values[:,0])
+    part[g] = e[g];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part[g] += __shfl_xor_sync(0xffffffffu, part[g], o);
   }
+  const float total = (part[0] + part[1]) + (part[2] + part[3]);
+#pragma unroll
+  for (int g = 0; g < EVAVOS_MAX_TOPK / 32; ++g) {
+    const int j = lane + 32 * g;
+    if (j < top_k) {
+      const bool live = j < take;
+      const int64_t o = q * top_k + j;
+      if (out_idx) out_idx[o] = live ? (int32_t)(0xffffffffu - (uint32_t)(sm.sel[j] & 0xffffffffull)) : -1;
+      if (out_weight) out_weight[o] = live ? e[g] / total : 0.f;
+      if (out_score) out_score[o] = live ? ordered_to_float((uint32_t)(sm.sel[j] >> 32)) : -INFINITY;
+    }
+  }
+  __syncwarp();
 }
 
 }  // namespace evavos

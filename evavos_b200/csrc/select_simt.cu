@@ -3,22 +3,18 @@
 //  brute_select_kernel  exact top-k of one query over ALL memory positions by a 4-round
 //                       8-bit radix select on order-preserving score keys (scores are
 //                       recomputed each round; no N-sized scratch).  It is the whole
-//                       selection in EVAVOS_PATH_SIMT and the overflow path of the tcgen05
-//                       filter (queries whose candidate list exceeded kCandCap, e.g. banks
-//                       with thousands of tied keys).
-//  finalize_kernel      exact rescoring of <= kCandCap candidates, top-k by (score desc,
-//                       position asc), softmax over the survivors
-//                       (softmax_w_g_top, prop_net.py:53-57).
+//                       selection in EVAVOS_PATH_SIMT (and for CK != 64).
+//  finalize_kernel      one warp per query: cuts a scored candidate list of the tcgen05 filter down with the
+//                       bound its own scores give, rescoring of the survivors in exact fp32, top-k by
+//                       (score desc, position asc), softmax over the survivors
+//                       (softmax_w_g_top, prop_net.py:53-57).  A query whose list overflowed (thousands of
+//                       tied keys) is redone exactly by the same warp (exact_topk_warp).
 //
-// All three agree on one arithmetic for a score: see dot_row / affinity_from_parts.
+// All of them agree on one arithmetic for a score: see dot_row / affinity_from_parts.
 #include "common.cuh"
 #include "select_common.cuh"
 
 namespace evavos {
-
-#ifdef EVAVOS_TRACE
-extern "C" int evavos_debug_fin_skip(int v) { return (int)cudaMemcpyToSymbol(g_fin_skip, &v, sizeof(int)); }
-#endif
 
 namespace {
 
@@ -53,8 +49,7 @@ __device__ __forceinline__ void score_group(const float* __restrict__ key_pm, in
 
 __global__ void __launch_bounds__(256) brute_select_kernel(
     const float* __restrict__ key_pm, const float* __restrict__ query, int64_t query_ch_stride, int CK,
-    int64_t n_pos, int64_t n_query, int top_k, int only_overflow, int32_t* __restrict__ cand,
-    int32_t* __restrict__ cand_cnt) {
+    int64_t n_pos, int64_t n_query, int top_k, int2* __restrict__ cand, int32_t* __restrict__ cand_cnt) {
   pdl_wait();
   pdl_launch_dependents();
   __shared__ __align__(16) float qs[kBruteQ][64];
@@ -76,7 +71,7 @@ __global__ void __launch_bounds__(256) brute_select_kernel(
     if (tid < kBruteQ) {
       const int64_t w = grp * kBruteQ + tid;
       int q = -1;
-      if (w < n_query && (!only_overflow || cand_cnt[w] > kCandCap)) q = (int)w;
+      if (w < n_query) q = (int)w;
       qid[tid] = q;
       remaining[tid] = top_k;
       prefix[tid] = 0;
@@ -84,12 +79,6 @@ __global__ void __launch_bounds__(256) brute_select_kernel(
       eq_base[tid] = 0;
     }
     __syncthreads();
-    {
-      bool any = false;
-#pragma unroll
-      for (int j = 0; j < kBruteQ; ++j) any |= qid[j] >= 0;
-      if (!any) continue;  // uniform: nothing overflowed in this group
-    }
     for (int e = tid; e < kBruteQ * 64; e += 256) {
       const int j = e >> 6, c = e & 63;
       const int q = qid[j];
@@ -159,7 +148,7 @@ __global__ void __launch_bounds__(256) brute_select_kernel(
         const uint32_t key = live ? float_to_ordered(s[j]) : 0u;
         if (live && key > T[j]) {
           const int pos = atomicAdd(&gt_cnt[j], 1);
-          cand[(int64_t)qid[j] * kCandCap + pos] = (int32_t)n;
+          cand[(int64_t)qid[j] * kCandCap + pos] = make_int2((int32_t)n, 0);
         }
         eq[j] = live && key == T[j];
         const unsigned m = __ballot_sync(0xffffffffu, eq[j]);
@@ -173,7 +162,7 @@ __global__ void __launch_bounds__(256) brute_select_kernel(
           if (eq[j]) {
             int r = eq_base[j] + rank[j];
             for (int w = 0; w < warp; ++w) r += warp_eq[w][j];
-            if (r < need[j]) cand[(int64_t)qid[j] * kCandCap + (top_k - need[j]) + r] = (int32_t)n;
+            if (r < need[j]) cand[(int64_t)qid[j] * kCandCap + (top_k - need[j]) + r] = make_int2((int32_t)n, 0);
           }
         }
         __syncthreads();
@@ -189,43 +178,44 @@ __global__ void __launch_bounds__(256) brute_select_kernel(
   }
 }
 
-// One 128-thread CTA per query (see finalize_query).  Measured on B200 at cfg2: 22 us with every thread walking its
-// own key row in global memory (L1/TEX 70 % busy: 32 partial lines per load instruction), 19.7 us with the rows
-// staged through shared memory by half-warps; one or four queries per CTA makes no difference.
-// only_flag != nullptr: only queries flagged there.
-__global__ void __launch_bounds__(128) finalize_kernel(
-    const float* __restrict__ key_pm, const float* __restrict__ query, int64_t query_ch_stride, int CK,
-    int64_t n_query, int top_k, const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
-    const int32_t* __restrict__ only_flag, int32_t* __restrict__ out_idx, float* __restrict__ out_weight,
+constexpr int kFinWarps = 4;   // queries per CTA
+
+// One warp per query (finalize_query_warp).  Round 1 ran one 128-thread CTA per query with an all-pairs rank over
+// ~70 candidates (17-19 us for 1 620 queries: a chain of dependent L2 round trips per CTA); a warp per query keeps
+// four independent chains per CTA in flight and needs no CTA barrier.
+__global__ void __launch_bounds__(32 * kFinWarps) finalize_kernel(
+    const float* __restrict__ key_pm, const float* __restrict__ query, int64_t query_ch_stride, int CK, int64_t n_pos,
+    int64_t n_query, int top_k, const int2* __restrict__ cand, const int32_t* __restrict__ cand_cnt, int scored,
+    const float* __restrict__ key_maxnorm, int32_t* __restrict__ out_idx, float* __restrict__ out_weight,
     float* __restrict__ out_score) {
-  __shared__ FinalizeSmem sm;
-  const int64_t q = blockIdx.x;
+  __shared__ FinalizeWarpSmem sm[kFinWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * kFinWarps + warp;
   pdl_wait();
   pdl_launch_dependents();
-  if (only_flag != nullptr && only_flag[q] == 0) return;
-  finalize_query(sm, threadIdx.x, q, key_pm, query, query_ch_stride, CK, top_k, cand, cand_cnt[q], out_idx,
-                 out_weight, out_score, [] { __syncthreads(); });
+  if (q >= n_query) return;
+  finalize_query_warp(sm[warp], lane, q, key_pm, query, query_ch_stride, CK, n_pos, top_k, cand, __ldcg(cand_cnt + q),
+                      scored, key_maxnorm, out_idx, out_weight, out_score);
 }
 
 }  // namespace
 
 int launch_brute_select(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_pos,
-                        int64_t n_query, int top_k, int only_overflow, int32_t* cand, int32_t* cand_cnt, int n_sm,
-                        cudaStream_t st) {
+                        int64_t n_query, int top_k, int2* cand, int32_t* cand_cnt, int n_sm, cudaStream_t st) {
+  (void)n_sm;
   int64_t grid = ceil_div(n_query, kBruteQ);
-  const int64_t cap = (int64_t)n_sm * 8;  // 8 resident 256-thread CTAs per SM
-  if (only_overflow && grid > cap) grid = cap;
   if (grid > 0x7fffffff) grid = 0x7fffffff;
   EVAVOS_CUDA_OK(launch_pdl(brute_select_kernel, dim3((unsigned)grid), dim3(256), 0, st, key_pm, query, query_ch_stride,
-                            CK, n_pos, n_query, top_k, only_overflow, cand, cand_cnt));
+                            CK, n_pos, n_query, top_k, cand, cand_cnt));
   return EVAVOS_OK;
 }
 
-int launch_finalize(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_query,
-                    int top_k, const int32_t* cand, const int32_t* cand_cnt, const int32_t* only_flag, int32_t* out_idx,
-                    float* out_weight, float* out_score, cudaStream_t st) {
-  EVAVOS_CUDA_OK(launch_pdl(finalize_kernel, dim3((unsigned)n_query), dim3(128), 0, st, key_pm, query, query_ch_stride,
-                            CK, n_query, top_k, cand, cand_cnt, only_flag, out_idx, out_weight, out_score));
+int launch_finalize(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_pos,
+                    int64_t n_query, int top_k, const int2* cand, const int32_t* cand_cnt, int scored,
+                    const float* key_maxnorm, int32_t* out_idx, float* out_weight, float* out_score, cudaStream_t st) {
+  EVAVOS_CUDA_OK(launch_pdl(finalize_kernel, dim3((unsigned)ceil_div(n_query, kFinWarps)), dim3(32 * kFinWarps), 0, st,
+                            key_pm, query, query_ch_stride, CK, n_pos, n_query, top_k, cand, cand_cnt, scored,
+                            key_maxnorm, out_idx, out_weight, out_score));
   return EVAVOS_OK;
 }
 

@@ -87,9 +87,13 @@ class InferenceCore:
         self._batch_frames = hasattr(prop_net, "decode_frames")
         self.key_batch = 16   # frames per key-encoder pass when a whole propagation pass is encoded ahead
         self._certain: MemoryBank | None = None
-        top_k = getattr(getattr(prop_net, "memory", None), "top_k", 50)
         mem = getattr(prop_net, "memory", None)
-        self._reader = mem if isinstance(mem, EvalMemoryReader) else EvalMemoryReader(top_k or 50, None)
+        top_k = getattr(mem, "top_k", 50)
+        if top_k is None:
+            raise NotImplementedError("prop_net.memory.top_k is None (full softmax over the bank): the reference never "
+                                      "runs it (PropagationNetwork(top_k=50), prop_net.py:141) and the fused read "
+                                      "implements the top-k form only")
+        self._reader = mem if isinstance(mem, EvalMemoryReader) else EvalMemoryReader(top_k, None)
 
     # ------------------------------------------------------------------ reference-layout views of certain memory
     @property
@@ -123,12 +127,14 @@ class InferenceCore:
         if len(missing) > 1 and self._batch_frames:
             batch = torch.cat([self.get_image_buffered(ti) for ti in missing], 0)
             outs = self.prop_net.encode_key(batch)
+            fresh = {}
             for j, ti in enumerate(missing):
                 if len(self.key_buf) > self.k_buf_size:
                     self.key_buf = {}
-                self.key_buf[ti] = tuple(o[j:j + 1] for o in outs)
-            if any(ti not in self.key_buf for ti in frames):   # the cache was flushed half-way: fall back
-                return [self.get_key_feat_buffered(ti) for ti in frames]
+                self.key_buf[ti] = fresh[ti] = tuple(o[j:j + 1] for o in outs)
+            # a small cache (mem_profile 2) may have been flushed half-way: hand out what was just computed
+            # instead of encoding those frames a second time
+            return [fresh[ti] if ti in fresh else self.get_key_feat_buffered(ti) for ti in frames]
         return [self.get_key_feat_buffered(ti) for ti in frames]
 
     # ------------------------------------------------------------------ pieces of segment_with_query
@@ -171,7 +177,6 @@ class InferenceCore:
         # pre-allocated bank, certain memory first (one import launch per tensor)
         bank = MemoryBank(K, CK, CV, H, W, total_m, self.device)
         bank.write_frames(0, certain.keys_view(), certain.values_view())
-        self._pass_bank = bank  # kept for inspection / tests; rebuilt every pass like the reference's locals
         last_ti = idx
         fuse = (closest_ti != self.t) and (closest_ti != -1)
 

@@ -13,6 +13,7 @@ accepts.  ``read`` is the fused fast path used by ``segment_with_query``.
 from __future__ import annotations
 
 import ctypes
+import os
 from collections import OrderedDict
 
 import torch
@@ -73,9 +74,14 @@ def _require_cuda(t: torch.Tensor, name: str):
 
 
 def memory_read(bank: MemoryBank, qk: torch.Tensor, top_k: int = 50, n_frames: int | None = None,
-                want_readout: bool = True, want_topk: bool = False, path: int = _lib.PATH_AUTO):
+                want_readout: bool = True, want_topk: bool = False, path: int = _lib.PATH_AUTO,
+                sample_stride: int | None = None, out: torch.Tensor | None = None):
     """Fused read of ``qk`` (1,CK,H,W) or (1,CK,F,H,W) against the first ``n_frames`` of ``bank``.
 
+    ``sample_stride`` (tensor path): the filter's threshold pass contracts every sample_stride-th key tile
+    (None/0: the library's choice, or $EVAVOS_SAMPLE_STRIDE when set - a tuning knob, results do not depend on it).
+    ``out``: optional pre-allocated fp32 destination viewed as (K, >=CV, nq) - e.g. the first CV channels of the
+    decoder's (K, 2*CV, H, W) input, so that no torch.cat is needed (prop_net.py:189-190).
     Returns (readout (K,CV,[F,]H,W) or None, TopKAffinity or None).
     """
     lib = _lib.load()
@@ -96,9 +102,18 @@ def memory_read(bank: MemoryBank, qk: torch.Tensor, top_k: int = 50, n_frames: i
     a.query = q2.data_ptr()
     a.query_ch_stride = q2.stride(0)
     a.n_pos, a.n_query, a.top_k, a.path = n_pos, nq, int(top_k), int(path)
-    out = idx = weight = score = None
+    a.sample_stride = int(sample_stride if sample_stride else os.environ.get("EVAVOS_SAMPLE_STRIDE", 0))
+    idx = weight = score = None
+    user_out = out
     if want_readout:
-        out = torch.empty((bank.K, bank.CV, nq), dtype=torch.float32, device=dev)
+        if out is None:
+            out = torch.empty((bank.K, bank.CV, nq), dtype=torch.float32, device=dev)
+        else:
+            # (K, C>=CV, *spatial) fp32 with contiguous positions: the kernel takes object / channel strides
+            if out.dtype != torch.float32 or out.device != dev or out.shape[0] != bank.K or out.shape[1] < bank.CV \
+                    or tuple(out.shape[2:]) != spatial or not out[0, 0].is_contiguous():
+                raise ValueError(f"out {tuple(out.shape)} cannot receive a ({bank.K},{bank.CV},{spatial}) readout")
+            a.readout_obj_stride, a.readout_ch_stride = out.stride(0), out.stride(1)
         a.readout = out.data_ptr()
     if want_topk:
         idx = torch.empty((nq, top_k), dtype=torch.int32, device=dev)
@@ -117,15 +132,17 @@ def memory_read(bank: MemoryBank, qk: torch.Tensor, top_k: int = 50, n_frames: i
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         _lib.check(lib.evavos_memread(ctypes.byref(a), _lib.current_stream_ptr(dev)))
     aff = TopKAffinity(idx, weight, score, n_pos, bank.H, bank.W) if want_topk else None
-    if out is not None:
-        out = out.view(bank.K, bank.CV, *spatial)
+    if want_readout:
+        out = out.view(bank.K, bank.CV, *spatial) if user_out is None else user_out[:, :bank.CV]
+    else:
+        out = None
     return out, aff
 
 
 class EvalMemoryReader(nn.Module):
     """Drop-in for prop_net.py:74-115 (``km`` Gaussian re-weighting is dead code upstream: km=None, :149)."""
 
-    def __init__(self, top_k, km=None):
+    def __init__(self, top_k, km=None, *, append_only=True):
         super().__init__()
         if km is not None:
             raise NotImplementedError("km (kernelised memory) is never enabled by the reference (prop_net.py:149)")
@@ -133,19 +150,50 @@ class EvalMemoryReader(nn.Module):
             raise NotImplementedError("top_k=None (full softmax) is not on the propagation path; see AttentionMemory")
         self.top_k = int(top_k)
         self.km = km
-        self._shadow_cache: "OrderedDict[tuple, MemoryBank]" = OrderedDict()
+        self.append_only = bool(append_only)
+        self._shadow_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
 
-    # ---- shadow of foreign reference-layout tensors, cached on (storage, version) -------------
+    # ---- shadow of foreign reference-layout tensors ------------------------------------------------
+    # A caller that keeps its bank as plain tensors (the reference's do_pass, inference_core.py:150-177) hands
+    # growing T-slices ``keys[:, :, :m_front]`` of ONE allocation to every read.  The shadow of such a bank is kept
+    # per allocation: the cache entry holds strong references to the source tensors (so their address cannot be
+    # recycled by the caching allocator while the entry lives - a recycled address with an equal version counter
+    # would otherwise alias another pass's bank) and remembers how many frames it has shadowed at which version.
+    # With ``append_only`` (the reference's contract: frames below m_front are never rewritten, :174-177) a longer
+    # slice of the same allocation only shadows the NEW frames; anything else rebuilds the shadow.
+    @staticmethod
+    def _alloc_sig(t):
+        return None if t is None else (t.data_ptr(), t.stride(0), t.stride(1), t.stride(2), t.stride(3), t.stride(4),
+                                       t.shape[0], t.shape[1], t.shape[3], t.shape[4], t.dtype)
+
     def _bank_for(self, mk: torch.Tensor, mv: torch.Tensor | None) -> MemoryBank:
-        def sig(t):
-            return None if t is None else (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t._version)
-        key = (sig(mk), sig(mv))
-        bank = self._shadow_cache.get(key)
-        if bank is None:
-            bank = MemoryBank.from_tensors(mk, mv)
-            self._shadow_cache[key] = bank
-            while len(self._shadow_cache) > 2:
-                self._shadow_cache.popitem(last=False)
+        key = (self._alloc_sig(mk), self._alloc_sig(mv))
+        t = mk.shape[2]
+        versions = (mk._version, None if mv is None else mv._version)
+        ent = self._shadow_cache.get(key)
+        if ent is not None:
+            bank, n_done, seen, _refs = ent
+            if seen == versions and n_done >= t:
+                self._shadow_cache.move_to_end(key)
+                bank.n_frames = t                       # a shorter slice of an unchanged bank reads a prefix
+                return bank
+            if self.append_only and n_done <= t and bank.capacity_frames >= t and n_done > 0:
+                if t > n_done:
+                    bank.n_frames = n_done
+                    bank.write_frames(n_done, mk[:, :, n_done:t], None if mv is None else mv[:, :, n_done:t])
+                bank.n_frames = t
+                self._shadow_cache[key] = (bank, t, versions, (mk, mv))
+                self._shadow_cache.move_to_end(key)
+                return bank
+        # capacity: whole allocation when the slice is a prefix view of a longer tensor (the base is visible)
+        base = mk._base if mk._base is not None and mk._base.dim() == 5 and mk._base.data_ptr() == mk.data_ptr() else None
+        cap = max(t, base.shape[2] if base is not None else t)
+        k, cv = (mv.shape[0], mv.shape[1]) if mv is not None else (0, 0)
+        bank = MemoryBank(k, mk.shape[1], cv, mk.shape[3], mk.shape[4], cap, mk.device, keep_reference_layout=False)
+        bank.write_frames(0, mk, mv)
+        self._shadow_cache[key] = (bank, t, versions, (mk, mv))
+        while len(self._shadow_cache) > 2:
+            self._shadow_cache.popitem(last=False)
         return bank
 
     def get_affinity(self, mk, qk) -> TopKAffinity:
@@ -183,7 +231,8 @@ class EvalMemoryReader(nn.Module):
 
     def _values_bank(self, mv: torch.Tensor) -> MemoryBank:
         key = ("v", mv.data_ptr(), tuple(mv.shape), tuple(mv.stride()), mv._version)
-        bank = self._shadow_cache.get(key)
+        ent = self._shadow_cache.get(key)
+        bank = ent[0] if ent is not None else None
         if bank is None:
             k, cv, t, h, w = mv.shape
             bank = MemoryBank(k, 8, cv, h, w, t, mv.device, keep_reference_layout=False)
@@ -196,7 +245,7 @@ class EvalMemoryReader(nn.Module):
                 _lib.check(lib.evavos_bank_write_values(ctypes.byref(sh), src.data_ptr(), src.stride(0), src.stride(1),
                                                         0, t * h * w, None, 0, 0, _lib.current_stream_ptr(mv.device)))
             bank.n_frames = t
-            self._shadow_cache[key] = bank
+            self._shadow_cache[key] = (bank, t, (mv._version,), (mv,))   # the reference pins the address
             while len(self._shadow_cache) > 2:
                 self._shadow_cache.popitem(last=False)
         return bank
@@ -214,6 +263,6 @@ class EvalMemoryReader(nn.Module):
         return self.read(mk, qk, mv)
 
     def __deepcopy__(self, memo):
-        new = EvalMemoryReader(self.top_k, self.km)
+        new = EvalMemoryReader(self.top_k, self.km, append_only=self.append_only)
         memo[id(self)] = new
         return new

@@ -278,18 +278,15 @@ class PropagationNetwork(nn.Module):
         return self.attn_memory(mk16, qk16)
 
     def get_attention(self, mk16, pos_mask, neg_mask, qk16):
-        """prop_net.py:198-211.  On CUDA tensors W = get_W(mk16, qk16) is never built: one fused attention read
-        (evavos_attention_readout) produces the stride-16 positive / negative maps directly."""
+        """prop_net.py:198-211.  W = get_W(mk16, qk16) is never built: one fused attention read
+        (evavos_attention_readout, CUDA tensors only - there is no CPU path) produces the stride-16 positive /
+        negative maps directly.  Any number of objects: the mask rows go through the kernel 32 at a time."""
         b, _, h, w = pos_mask.shape
         nh, nw = h // 16, w // 16
         pos = F.interpolate(pos_mask, size=(nh, nw), mode="area").view(b, 1, nh * nw)
         neg = F.interpolate(neg_mask, size=(nh, nw), mode="area").view(b, 1, nh * nw)
-        if mk16.is_cuda:
-            from .attention import attention_readout
-            attn = attention_readout(mk16, qk16, torch.cat([pos, neg], 1).view(2 * b, nh * nw)).view(b, 2, nh, nw)
-        else:  # module definition on CPU tensors (state-dict / shape tests); not a product path
-            W = self.get_W(mk16, qk16)
-            attn = torch.cat([pos @ W, neg @ W], 1).reshape(b, 2, nh, nw)
+        from .attention import attention_readout
+        attn = attention_readout(mk16, qk16, torch.cat([pos, neg], 1).view(2 * b, nh * nw)).view(b, 2, nh, nw)
         return F.interpolate(attn, mode="bilinear", size=(h, w), align_corners=False)
 
 

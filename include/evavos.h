@@ -117,7 +117,8 @@ typedef struct EvavosMemReadArgs {
   int32_t top_k;
   int32_t path;            /* EVAVOS_PATH_*                                           */
   int32_t n_sm;            /* SM count to size grids for (0 -> query the device)      */
-  int32_t reserved;
+  int32_t sample_stride;   /* tensor path: the threshold pass contracts every sample_stride-th key tile
+                              (0 -> the library's choice; 1 = two full sweeps; clamped for short banks) */
 } EvavosMemReadArgs;
 
 int evavos_abi_version(void);
@@ -134,8 +135,8 @@ size_t evavos_key_tiles_bytes(int64_t capacity_pos);
  *        inference_core.py:175, or a T-slice of an existing bank).
  *   dst_ref: optional reference-layout bank keys (1,CK,T,H,W); element
  *        [c*dst_ref_ch_stride + pos0 + i] receives src[c][i].  NULL to skip.
- * Updates key_pm, key_tiles (if non-NULL) and key_maxnorm of `bank`.
- * When the written range ends inside a tile, the tile's remaining rows are marked empty.
+ * Updates key_pm, key_tiles (if non-NULL) and key_maxnorm of `bank`.  Only the rows of the written range
+ * change: any slot may be rewritten in place (the read ignores tile rows at or beyond its n_pos).
  */
 int evavos_bank_write_keys(const EvavosBankShadow* bank, const float* src, int64_t src_ch_stride,
                            int64_t pos0, int64_t n_pos, float* dst_ref, int64_t dst_ref_ch_stride,
@@ -226,9 +227,11 @@ int evavos_memread_host(const float* mem_key, const float* query, const float* m
                         int64_t* d2h_bytes);
 
 /*
- * Diagnostics: when enabled, evavos_memread records CUDA events between its stages on the caller's stream;
- * evavos_stage_timing_read waits for the last call and returns ms of {candidate filter, exact-select fallback,
- * finalize, readout}.  Not thread-safe; off by default.
+ * Diagnostics: when enabled, evavos_memread records CUDA events between its stages on the caller's stream (a ring
+ * of 256 sets: no synchronisation between calls); evavos_stage_timing_read waits for the newest call and returns
+ * the mean ms of {candidate selection, 0 (unused), finalize, readout} over the calls since the last read.
+ * The event records sit between the kernels and defeat their programmatic-dependent-launch overlap, so the stage
+ * times add up to more than an un-instrumented call.  Process-wide, not thread-safe; off by default.
  */
 int evavos_stage_timing(int32_t enable);
 int evavos_stage_timing_read(float* ms4);

@@ -2,7 +2,7 @@
 import ctypes, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["EVAVOS_LIB"] = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "evavos_b200", "libevavos_sm100_trace.so")
+os.environ.setdefault("EVAVOS_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "evavos_b200", "libevavos_sm100_trace.so"))
 import evavos_b200 as ev
 from evavos_b200 import _lib
 from bench import WORKLOADS, synth
@@ -35,17 +35,24 @@ for _ in range(2):
         ev.memory_read(bank, qk, 50, want_readout=False, want_topk=True)
 torch.cuda.synchronize()
 lib = _lib.load()
+i0 = int(os.environ.get("TRACE_I0", "0"))
+if i0:
+    lib.evavos_debug_trace_base.argtypes = [ctypes.c_int]
+    lib.evavos_debug_trace_base(i0)
+    ev.memory_read(bank, qk, 50, want_readout=False, want_topk=True)
+    torch.cuda.synchronize()
+print("trace window starts at iteration", i0)
 buf = (ctypes.c_longlong * (6 * 64))()
 lib.evavos_debug_trace.argtypes = [ctypes.c_void_p]
 print("rc", lib.evavos_debug_trace(buf))
 tr = np.array(list(buf), dtype=np.int64).reshape(6, 64)
-t0 = tr[1, 0]
+t0 = tr[1, 0] if i0 == 0 else tr[0, 57]
 names = ["prod_issue", "mma_ready", "mma_issued", "epi_accfull", "epi_ldtm_done", "epi_math_done"]
 print("tile " + " ".join(f"{n:>13s}" for n in names))
 for i in range(0, 40):
     print(f"{i:4d} " + " ".join(f"{int(tr[r, i] - t0):13d}" for r in range(6)))
 print("kernel marks (entry, roles start, end sweep2, exit):", [int(x - t0) for x in tr[0, 56:60]])
-print("phase marks (end sweep1, after barrier1, after thresholds, after barrier2):", [int(x - t0) for x in tr[0, 60:64]])
+print("phase marks (end phase A, after barrier1, after thresholds, after barrier2):", [int(x - t0) for x in tr[0, 60:64]])
 d = np.diff(tr[:, 8:40], axis=1)
 print("mean cycles/tile (tiles 8..40):", {n: float(d[r].mean()) for r, n in enumerate(names)})
 print("mma_ready -> issued", float((tr[2, 8:40] - tr[1, 8:40]).mean()), " accfull -> ldtm", float((tr[4, 8:40] - tr[3, 8:40]).mean()),

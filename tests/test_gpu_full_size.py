@@ -1,7 +1,7 @@
 """GPU: BASELINE.json's full sizes, checked through size-independent properties and a sampled fp64 oracle.
 
 At cfg2 (N = 32 400, 3 objects) and cfg4 (N = 324 000) the CPU oracle is too slow to run in full, so:
-  * for a sample of queries the exact fp64 affinity against ALL positions is computed (numpy, 64-dim dots) and the
+  * for a sample of >= 256 queries the exact fp64 affinity against ALL positions is computed (numpy, 64-dim dots) and the
     selected set must be the true top-50 (near-ties classified with TIE_TOL);
   * every query: 50 distinct in-range positions, best-first scores, weights = softmax(scores), sum 1;
   * the readout equals the weighted gather of the selected rows (sampled), and is linear in the values.
@@ -26,7 +26,10 @@ def test_full_size_properties(name, t, k):
     bank = ev.MemoryBank(k, ck, cv, h, w, t, dev, keep_reference_layout=False)
     bank.write_frames(0, mk.to(dev), mv.to(dev))
     out, aff = ev.memory_read(bank, qk.to(dev), 50, want_topk=True)
+    # every query: the tcgen05 filter + exact rescoring selects what the exact CUDA-core selection selects
+    _, aff_x = ev.memory_read(bank, qk.to(dev), 50, want_readout=False, want_topk=True, path=ev._lib.PATH_SIMT)
     torch.cuda.synchronize()
+    assert torch.equal(aff.idx, aff_x.idx) and torch.equal(aff.weight, aff_x.weight)
     idx, wgt, sc = aff.idx.cpu().numpy(), aff.weight.cpu().numpy(), aff.score.cpu().numpy()
     out = out.cpu().numpy().reshape(k, cv, hw)
     # structure
@@ -38,7 +41,8 @@ def test_full_size_properties(name, t, k):
     assert np.abs(wgt.sum(1) - 1).max() < 1e-5
     # sampled exact check against all N positions
     rng = np.random.default_rng(0)
-    sample = np.sort(rng.choice(hw, 48, replace=False))
+    # >= 256 queries, the last (partial) 128-row query tile included
+    sample = np.unique(np.concatenate([rng.choice(hw, 256, replace=False), np.arange(hw - 84, hw, 4), [0, hw - 1]]))
     mkf = mk[0].reshape(ck, n).numpy()
     s64 = onp.affinity_scores(mkf, qk[0].reshape(ck, hw).numpy()[:, sample])
     exact, tie, bad, bad_q = onp.compare_topk(idx[sample], s64, 50, TIE_TOL)

