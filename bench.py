@@ -378,17 +378,21 @@ def run_sharded(args, cfg, rank, world, local_rank, dist=None, emit=True):
     stream = torch.cuda.current_stream(dev)
 
     def step(i):
-        # mem_freq = 5 query frames share one bank state (inference_core.py:174): one exchange for all of them
-        return banks[i % n_banks].read(queries[i % n_banks], TOP_K)
+        # mem_freq = 5 query frames share one bank state (inference_core.py:174): one exchange for all of them;
+        # every rank ends with the readout of the query slice it owns (the decoder consumes it where it is)
+        return banks[i % n_banks].read(queries[i % n_banks], TOP_K, scatter=True)
 
     def step_single(i):
         return ev.memory_read(full[0], queries[i % n_banks], TOP_K)[0]
 
     # parity: every rank's sharded result against its own single-bank read of the same bank
-    out_s, idx_s, w_s = banks[0].read(queries[0], TOP_K, return_topk=True)
+    from evavos_b200.sharded import query_slice
+    out_s, idx_s, w_s = banks[0].read(queries[0], TOP_K, return_topk=True, scatter=True)
     out_1, aff_1 = ev.memory_read(full[0], queries[0], TOP_K, want_topk=True)
     torch.cuda.synchronize(dev)
-    rel = float(((out_s - out_1).norm() / out_1.norm()).item())
+    q0, q1 = query_slice(MEM_FREQ * hw, rank, world)
+    ref_slice = out_1.reshape(k, cv, MEM_FREQ * hw)[:, :, q0:q1]
+    rel = float(((out_s - ref_slice).norm() / ref_slice.norm()).item())
     same_idx = bool(torch.equal(idx_s, aff_1.idx))
     parity = torch.tensor([1.0 if (rel < 1e-5 and same_idx) else 0.0, rel], device=dev, dtype=torch.float64)
 
@@ -413,7 +417,7 @@ def run_sharded(args, cfg, rank, world, local_rank, dist=None, emit=True):
         tm = torch.tensor([elapsed_ms, single_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         elapsed_ms, single_ms = float(tm[0].item()), float(tm[1].item())
-        dist.all_reduce(parity, op=dist.ReduceOp.MIN if False else dist.ReduceOp.MAX)   # worst rel error
+        dist.all_reduce(parity, op=dist.ReduceOp.MAX)   # worst rel error over the ranks
         ok = torch.tensor([1.0 if (rel < 1e-5 and same_idx) else 0.0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         parity_ok = bool(ok.item() > 0.5)

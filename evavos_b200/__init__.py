@@ -11,9 +11,11 @@ from .aggregate import aggregate_wbg, argmax_unpad, get_segmentations
 from .attention import attention_readout
 from .memory_bank import MemoryBank
 from .memory_reader import EvalMemoryReader, TopKAffinity, memory_read
+from .metrics import eval_processor_metric, frame_metrics, get_j_and_f
 from .networks import FusionNet, PropagationNetwork
 from .inference_core import InferenceCore
 from .tensor_util import pad_divide_by
 
 __all__ = ["EvavosError", "aggregate_wbg", "argmax_unpad", "get_segmentations", "attention_readout", "MemoryBank", "EvalMemoryReader", "TopKAffinity", "memory_read",
-           "PropagationNetwork", "FusionNet", "InferenceCore", "pad_divide_by", "_lib"]
+           "PropagationNetwork", "FusionNet", "InferenceCore", "pad_divide_by", "_lib",
+           "eval_processor_metric", "frame_metrics", "get_j_and_f"]

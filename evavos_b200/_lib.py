@@ -10,7 +10,7 @@ import ctypes
 import os
 import threading
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 F32, BF16 = 0, 1
 PATH_AUTO, PATH_TENSOR, PATH_SIMT = 0, 1, 2
 TILE_POS = 128
@@ -33,6 +33,14 @@ class BankShadow(ctypes.Structure):
     ]
 
 
+MAX_RANKS = 16
+
+
+class Peers(ctypes.Structure):
+    """struct EvavosPeers (include/evavos.h)."""
+    _fields_ = [("n_ranks", _c_i32), ("rank", _c_i32), ("base", _c_vp * MAX_RANKS)]
+
+
 class MemReadArgs(ctypes.Structure):
     """struct EvavosMemReadArgs (include/evavos.h)."""
     _fields_ = [
@@ -42,6 +50,7 @@ class MemReadArgs(ctypes.Structure):
         ("workspace_bytes", _c_i64), ("n_pos", _c_i64), ("n_query", _c_i64), ("query_ch_stride", _c_i64),
         ("readout_obj_stride", _c_i64), ("readout_ch_stride", _c_i64),
         ("top_k", _c_i32), ("path", _c_i32), ("n_sm", _c_i32), ("sample_stride", _c_i32),
+        ("peers", ctypes.POINTER(Peers)), ("peer_gather_offset", _c_i64),
     ]
 
 
@@ -58,6 +67,11 @@ SIGNATURES = {
     "evavos_memread_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(MemReadArgs)]),
     "evavos_memread": (_c_i32, [ctypes.POINTER(MemReadArgs), _c_vp]),
     "evavos_readout": (_c_i32, [ctypes.POINTER(BankShadow), _c_vp, _c_vp, _c_i64, _c_i32, _c_vp, _c_i64, _c_i64, _c_vp]),
+    "evavos_readout_qmajor": (_c_i32, [ctypes.POINTER(BankShadow), _c_vp, _c_vp, _c_i64, _c_i32, _c_vp, _c_vp]),
+    "evavos_peer_barrier": (_c_i32, [ctypes.POINTER(Peers), _c_i64, ctypes.c_uint32, _c_vp]),
+    "evavos_peer_reduce_scatter": (_c_i32, [ctypes.POINTER(Peers), _c_i64, _c_i32, _c_i64, _c_i64, _c_vp, _c_i64, _c_vp]),
+    "evavos_jf_workspace_bytes": (ctypes.c_size_t, [_c_i64, _c_i32, _c_i32]),
+    "evavos_jf_metrics": (_c_i32, [_c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_i32, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp]),
     "evavos_affinity_dense": (_c_i32, [_c_vp, _c_vp, _c_i64, _c_i32, _c_i64, _c_vp, _c_vp]),
     "evavos_aggregate_wbg": (_c_i32, [_c_vp, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_vp]),
     "evavos_argmax_unpad": (_c_i32, [_c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_vp, _c_vp, _c_i32, _c_i32, _c_i32, _c_i32, _c_vp]),

@@ -97,6 +97,17 @@ int validate_bank(const EvavosBankShadow* b) {
   return EVAVOS_OK;
 }
 
+int validate_peers(const EvavosPeers* p) {
+  if (!p) { set_error("peers is NULL"); return EVAVOS_ERR_INVALID; }
+  if (p->n_ranks < 1 || p->n_ranks > EVAVOS_MAX_RANKS || p->rank < 0 || p->rank >= p->n_ranks) {
+    set_error("peers: n_ranks=%d rank=%d out of range (1..%d)", p->n_ranks, p->rank, EVAVOS_MAX_RANKS);
+    return EVAVOS_ERR_INVALID;
+  }
+  for (int g = 0; g < p->n_ranks; ++g)
+    if (!p->base[g]) { set_error("peers: base[%d] is NULL", g); return EVAVOS_ERR_INVALID; }
+  return EVAVOS_OK;
+}
+
 int validate_read(const EvavosMemReadArgs* a) {
   if (!a) { set_error("args is NULL"); return EVAVOS_ERR_INVALID; }
   int rc = validate_bank(&a->bank);
@@ -118,6 +129,11 @@ int validate_read(const EvavosMemReadArgs* a) {
     return EVAVOS_ERR_UNSUPPORTED;
   }
   if (a->readout && (!a->bank.val_pm || a->bank.K <= 0)) { set_error("readout requested without values"); return EVAVOS_ERR_INVALID; }
+  if (a->peers != nullptr) {
+    int rc2 = validate_peers(a->peers);
+    if (rc2) return rc2;
+    if (a->peer_gather_offset < 0 || (a->peer_gather_offset % 8) != 0) { set_error("peer_gather_offset must be a non-negative multiple of 8"); return EVAVOS_ERR_INVALID; }
+  }
   return EVAVOS_OK;
 }
 
@@ -267,7 +283,8 @@ int evavos_memread(const EvavosMemReadArgs* a, evavos_stream_t stream) {
   // 2. tightening of the list (tensor path), exact rescoring, top-k, softmax; a query whose list overflowed
   //    (massive ties) is redone exactly inside the same kernel
   rc = launch_finalize(a->bank.key_pm, a->query, a->query_ch_stride, CK, a->n_pos, a->n_query, a->top_k, c.sb.cand,
-                       c.sb.cand_cnt, tensor ? 1 : 0, a->bank.key_maxnorm, idx, weight, a->topk_score, st);
+                       c.sb.cand_cnt, tensor ? 1 : 0, a->bank.key_maxnorm, idx, weight, a->topk_score, a->peers,
+                       a->peer_gather_offset, st);
   if (rc) return rc;
   stage_mark(3, st);
 
@@ -292,6 +309,54 @@ int evavos_readout(const EvavosBankShadow* bank, const int32_t* idx, const float
     return EVAVOS_ERR_INVALID;
   }
   return launch_readout(*bank, idx, weight, n_query, top_k, out, out_obj_stride, out_ch_stride, (cudaStream_t)stream);
+}
+
+int evavos_readout_qmajor(const EvavosBankShadow* bank, const int32_t* idx, const float* weight, int64_t n_query,
+                          int32_t top_k, float* out, evavos_stream_t stream) {
+  int rc = validate_bank(bank);
+  if (rc) return rc;
+  if (!bank->val_pm || !idx || !weight || !out || n_query <= 0 || top_k <= 0 || top_k > EVAVOS_MAX_TOPK ||
+      (reinterpret_cast<uintptr_t>(out) % 16) != 0) {
+    set_error("readout_qmajor: bad arguments");
+    return EVAVOS_ERR_INVALID;
+  }
+  return launch_readout(*bank, idx, weight, n_query, top_k, out, 0, -1, (cudaStream_t)stream);
+}
+
+int evavos_peer_barrier(const EvavosPeers* peers, int64_t flag_offset, uint32_t epoch, evavos_stream_t stream) {
+  int rc = validate_peers(peers);
+  if (rc) return rc;
+  if (flag_offset < 0 || (flag_offset % 4) != 0) { set_error("peer_barrier: bad flag_offset"); return EVAVOS_ERR_INVALID; }
+  return launch_peer_barrier(*peers, flag_offset, epoch, (cudaStream_t)stream);
+}
+
+int evavos_peer_reduce_scatter(const EvavosPeers* peers, int64_t partial_offset, int32_t rows, int64_t q0, int64_t q1,
+                               float* out, int64_t out_row_stride, evavos_stream_t stream) {
+  int rc = validate_peers(peers);
+  if (rc) return rc;
+  if (!out || rows <= 0 || (rows % 4) != 0 || q0 < 0 || q1 < q0 || partial_offset < 0 || (partial_offset % 16) != 0) {
+    set_error("peer_reduce_scatter: bad arguments (rows must be a multiple of 4, offsets 16-byte aligned)");
+    return EVAVOS_ERR_INVALID;
+  }
+  return launch_peer_reduce_scatter(*peers, partial_offset, rows, q0, q1, out, out_row_stride, (cudaStream_t)stream);
+}
+
+size_t evavos_jf_workspace_bytes(int64_t T, int32_t h, int32_t w) {
+  if (T <= 0 || h <= 0 || w <= 0) return 0;
+  return jf_workspace_bytes(T, h, w);
+}
+
+int evavos_jf_metrics(const uint8_t* pred, const uint8_t* gt, int64_t T, int32_t h, int32_t w, int32_t bound_pix,
+                      void* workspace, int64_t workspace_bytes, double* out, int32_t* gt_empty, evavos_stream_t stream) {
+  if (!pred || !gt || !out || !workspace || T <= 0 || h <= 0 || w <= 0) {
+    set_error("jf_metrics: bad arguments");
+    return EVAVOS_ERR_INVALID;
+  }
+  if (workspace_bytes < (int64_t)jf_workspace_bytes(T, h, w)) {
+    set_error("jf_metrics: workspace of %lld bytes, %zu needed", (long long)workspace_bytes, jf_workspace_bytes(T, h, w));
+    return EVAVOS_ERR_WORKSPACE;
+  }
+  return launch_jf_metrics(pred, gt, T, h, w, bound_pix, workspace, out, gt_empty, (cudaStream_t)stream);
 }
 
 int evavos_affinity_dense(const int32_t* idx, const float* weight, int64_t n_query, int32_t top_k, int64_t n_pos,

@@ -70,6 +70,10 @@ __host__ __device__ __forceinline__ float ordered_to_float(uint32_t k) {
 #endif
 }
 
+__device__ __forceinline__ uint32_t ordered_to_float_bits(uint32_t k) {
+  return (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+}
+
 // Byte offset of (row r, 16-byte chunk c) inside a 128B-swizzled K-major tile (Swizzle<3,4,3>).
 __host__ __device__ __forceinline__ int swizzle128_offset(int r, int c) {
   return r * 128 + (((c ^ (r & 7)) & 7) << 4);
@@ -120,7 +124,14 @@ int launch_brute_select(const float* key_pm, const float* query, int64_t query_c
 // scores themselves give; key_maxnorm is only read then.
 int launch_finalize(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_pos,
                     int64_t n_query, int top_k, const int2* cand, const int32_t* cand_cnt, int scored,
-                    const float* key_maxnorm, int32_t* out_idx, float* out_weight, float* out_score, cudaStream_t st);
+                    const float* key_maxnorm, int32_t* out_idx, float* out_weight, float* out_score,
+                    const EvavosPeers* peers, int64_t peer_gather_offset, cudaStream_t st);
+size_t jf_workspace_bytes(int64_t T, int h, int w);
+int launch_jf_metrics(const uint8_t* pred, const uint8_t* gt, int64_t T, int h, int w, int radius, void* workspace,
+                      double* out, int32_t* gt_empty, cudaStream_t st);
+int launch_peer_barrier(const EvavosPeers& peers, int64_t flag_offset, uint32_t epoch, cudaStream_t st);
+int launch_peer_reduce_scatter(const EvavosPeers& peers, int64_t partial_offset, int rows, int64_t q0, int64_t q1,
+                               float* out, int64_t out_row_stride, cudaStream_t st);
 int launch_score_select(const float* query, int64_t query_ch_stride, const void* key_tiles, const float* key_maxnorm,
                         int64_t n_pos, int64_t n_query, int top_k, int n_chunks, int sample_stride, int n_sm,
                         float* class_max, float* tau, int2* cand, int32_t* cand_cnt, void* strip,

@@ -27,7 +27,9 @@ __device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
 
 // fp32 rows; each CTA covers 128 * NV channels starting at blockIdx.z * 128 * NV of rows that are CV floats long.
 // grid (ceil(nq/8), K, CV / (128 * NV)), 256 threads.
-template <int NV>
+// QMAJOR: the output is (n_query, K, CV) - one contiguous K*CV row per query, written straight from the registers
+// (the layout the sharded read reduces over: a query slice is a contiguous chunk); out_*_stride are ignored.
+template <int NV, bool QMAJOR>
 __global__ void __launch_bounds__(256) readout_f32_kernel(
     const float* __restrict__ val_pm_all, int64_t capacity_pos, int CVfull, const int32_t* __restrict__ idx,
     const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out_all,
@@ -63,6 +65,14 @@ __global__ void __launch_bounds__(256) readout_f32_kernel(
       }
     }
   }
+  if constexpr (QMAJOR) {
+    if (q < n_query) {
+      float* row = out_all + ((int64_t)q * gridDim.y + o) * CVfull + (int64_t)blockIdx.z * CV;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(row + i * 128 + lane * 4) = acc[i];
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = i * 128 + lane * 4;
@@ -80,7 +90,7 @@ __global__ void __launch_bounds__(256) readout_f32_kernel(
 }
 
 // bf16 rows, CV = 256 * NV (8 bf16 per 16-byte load), fp32 accumulation.
-template <int NV>
+template <int NV, bool QMAJOR>
 __global__ void __launch_bounds__(256) readout_bf16_kernel(
     const __nv_bfloat16* __restrict__ val_pm, int64_t capacity_pos, const int32_t* __restrict__ idx,
     const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out,
@@ -124,6 +134,17 @@ __global__ void __launch_bounds__(256) readout_bf16_kernel(
       }
     }
   }
+  if constexpr (QMAJOR) {
+    if (q < n_query) {
+      float* row = out + ((int64_t)q * gridDim.y + o) * CV;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        *reinterpret_cast<float4*>(row + i * 256 + lane * 8) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        *reinterpret_cast<float4*>(row + i * 256 + lane * 8 + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < NV; ++i)
 #pragma unroll
@@ -164,7 +185,8 @@ __global__ void __launch_bounds__(128) readout_generic_kernel(
       else v = vbase[(int64_t)n * CV + c];
       acc = fmaf(s_w[j], v, acc);
     }
-    out[(int64_t)o * out_obj_stride + (int64_t)c * out_ch_stride + q] = acc;
+    if (out_ch_stride < 0) out[((int64_t)q * gridDim.y + o) * CV + c] = acc;   // query-major (see launch_readout)
+    else out[(int64_t)o * out_obj_stride + (int64_t)c * out_ch_stride + q] = acc;
   }
 }
 
@@ -179,21 +201,25 @@ __global__ void scatter_dense_kernel(const int32_t* __restrict__ idx, const floa
 
 }  // namespace
 
+// out_ch_stride < 0 selects the query-major output (n_query, K, CV).
 int launch_readout(const EvavosBankShadow& b, const int32_t* idx, const float* weight, int64_t n_query,
                    int top_k, float* out, int64_t out_obj_stride, int64_t out_ch_stride, cudaStream_t st) {
   if (n_query <= 0) return EVAVOS_OK;
+  const bool qmajor = out_ch_stride < 0;
   if (out_ch_stride == 0) out_ch_stride = n_query;
   if (out_obj_stride == 0) out_obj_stride = (int64_t)b.CV * n_query;
   const dim3 grid((unsigned)ceil_div(n_query, kQPerCta), (unsigned)b.K);
   const bool row16 = (reinterpret_cast<uintptr_t>(b.val_pm) % 16) == 0;
-#define EVAVOS_RO_F32(NV, SPLIT)                                                                              \
-  EVAVOS_CUDA_OK(launch_pdl(readout_f32_kernel<NV>, dim3(grid.x, grid.y, SPLIT), dim3(256), 0, st,            \
+#define EVAVOS_RO_F32_(NV, SPLIT, QM)                                                                         \
+  EVAVOS_CUDA_OK(launch_pdl(readout_f32_kernel<NV, QM>, dim3(grid.x, grid.y, SPLIT), dim3(256), 0, st,        \
                             reinterpret_cast<const float*>(b.val_pm), b.capacity_pos, b.CV, idx, weight,      \
                             n_query, top_k, out, out_obj_stride, out_ch_stride))
-#define EVAVOS_RO_BF16(NV)                                                                                    \
-  EVAVOS_CUDA_OK(launch_pdl(readout_bf16_kernel<NV>, grid, dim3(256), 0, st,                                  \
+#define EVAVOS_RO_F32(NV, SPLIT) do { if (qmajor) EVAVOS_RO_F32_(NV, SPLIT, true); else EVAVOS_RO_F32_(NV, SPLIT, false); } while (0)
+#define EVAVOS_RO_BF16_(NV, QM)                                                                               \
+  EVAVOS_CUDA_OK(launch_pdl(readout_bf16_kernel<NV, QM>, grid, dim3(256), 0, st,                              \
                             reinterpret_cast<const __nv_bfloat16*>(b.val_pm), b.capacity_pos, idx, weight,    \
                             n_query, top_k, out, out_obj_stride, out_ch_stride))
+#define EVAVOS_RO_BF16(NV) do { if (qmajor) EVAVOS_RO_BF16_(NV, true); else EVAVOS_RO_BF16_(NV, false); } while (0)
   if (b.val_dtype == EVAVOS_F32 && row16 && b.CV % 128 == 0 && b.CV <= 512) {
     // Splitting a row's channels over two CTAs (more resident warps) was measured SLOWER on B200 (55 vs 42 us at
     // cfg2: twice the L2 requests at half the size), so one warp keeps a whole value row.
@@ -219,7 +245,9 @@ int launch_readout(const EvavosBankShadow& b, const int32_t* idx, const float* w
                                                         out_ch_stride);
   }
 #undef EVAVOS_RO_F32
+#undef EVAVOS_RO_F32_
 #undef EVAVOS_RO_BF16
+#undef EVAVOS_RO_BF16_
   EVAVOS_CUDA_OK(cudaGetLastError());
   return EVAVOS_OK;
 }

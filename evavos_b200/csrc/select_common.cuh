@@ -72,6 +72,13 @@ __device__ __forceinline__ unsigned long long score_key(float s, int32_t n) {
   return ((unsigned long long)float_to_ordered(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
 }
 
+// Sharded read: the gather regions of all ranks (see EvavosMemReadArgs.peers); n_ranks == 0 when not sharded.
+struct PeerPush {
+  int n_ranks;
+  int rank;
+  int2* dst[EVAVOS_MAX_RANKS];   // rank g's region [n_ranks][n_query][top_k] of (local position, score bits)
+};
+
 // Per-warp scratch of the finalizer (one warp finalizes one query).
 struct FinalizeWarpSmem {
   float qs[64];
@@ -183,7 +190,8 @@ __device__ __forceinline__ void finalize_query_warp(FinalizeWarpSmem& sm, int la
                                                     const int2* __restrict__ cand, int cnt_raw, int scored,
                                                     const float* __restrict__ key_maxnorm,
                                                     int32_t* __restrict__ out_idx, float* __restrict__ out_weight,
-                                                    float* __restrict__ out_score) {
+                                                    float* __restrict__ out_score, const PeerPush& push,
+                                                    int64_t n_query) {
   sm.qs[lane] = (lane < CK) ? __ldg(query + (int64_t)lane * query_ch_stride + q) : 0.f;
   sm.qs[lane + 32] = (lane + 32 < CK) ? __ldg(query + (int64_t)(lane + 32) * query_ch_stride + q) : 0.f;
   __syncwarp();
@@ -283,6 +291,18 @@ __device__ __forceinline__ void finalize_query_warp(FinalizeWarpSmem& sm, int la
       if (out_idx) out_idx[o] = live ? (int32_t)(0xffffffffu - (uint32_t)(sm.sel[j] & 0xffffffffull)) : -1;
       if (out_weight) out_weight[o] = live ? e[g] / total : 0.f;
       if (out_score) out_score[o] = live ? ordered_to_float((uint32_t)(sm.sel[j] >> 32)) : -INFINITY;
+    }
+  }
+  // Sharded read: this query's list goes straight into every rank's gather region (stores over NVLink peer
+  // memory) - the all-gather happens here, query by query, while the other queries are still being finalized.
+  if (push.n_ranks > 0) {
+    for (int g = 0; g < push.n_ranks; ++g) {
+      int2* row = push.dst[g] + ((int64_t)push.rank * n_query + q) * top_k;
+      for (int j = lane; j < top_k; j += 32) {
+        const bool live = j < take;
+        row[j] = make_int2(live ? (int32_t)(0xffffffffu - (uint32_t)(sm.sel[j] & 0xffffffffull)) : -1,
+                           live ? (int32_t)ordered_to_float_bits((uint32_t)(sm.sel[j] >> 32)) : (int32_t)0xff800000u);
+      }
     }
   }
   __syncwarp();

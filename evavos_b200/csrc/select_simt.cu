@@ -11,6 +11,8 @@
 //                       tied keys) is redone exactly by the same warp (exact_topk_warp).
 //
 // All of them agree on one arithmetic for a score: see dot_row / affinity_from_parts.
+#include <cstring>
+
 #include "common.cuh"
 #include "select_common.cuh"
 
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(32 * kFinWarps) finalize_kernel(
     const float* __restrict__ key_pm, const float* __restrict__ query, int64_t query_ch_stride, int CK, int64_t n_pos,
     int64_t n_query, int top_k, const int2* __restrict__ cand, const int32_t* __restrict__ cand_cnt, int scored,
     const float* __restrict__ key_maxnorm, int32_t* __restrict__ out_idx, float* __restrict__ out_weight,
-    float* __restrict__ out_score) {
+    float* __restrict__ out_score, const PeerPush push) {
   __shared__ FinalizeWarpSmem sm[kFinWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * kFinWarps + warp;
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(32 * kFinWarps) finalize_kernel(
   pdl_launch_dependents();
   if (q >= n_query) return;
   finalize_query_warp(sm[warp], lane, q, key_pm, query, query_ch_stride, CK, n_pos, top_k, cand, __ldcg(cand_cnt + q),
-                      scored, key_maxnorm, out_idx, out_weight, out_score);
+                      scored, key_maxnorm, out_idx, out_weight, out_score, push, n_query);
 }
 
 }  // namespace
@@ -212,10 +214,19 @@ int launch_brute_select(const float* key_pm, const float* query, int64_t query_c
 
 int launch_finalize(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_pos,
                     int64_t n_query, int top_k, const int2* cand, const int32_t* cand_cnt, int scored,
-                    const float* key_maxnorm, int32_t* out_idx, float* out_weight, float* out_score, cudaStream_t st) {
+                    const float* key_maxnorm, int32_t* out_idx, float* out_weight, float* out_score,
+                    const EvavosPeers* peers, int64_t peer_gather_offset, cudaStream_t st) {
+  PeerPush push;
+  memset(&push, 0, sizeof(push));
+  if (peers != nullptr) {
+    push.n_ranks = peers->n_ranks;
+    push.rank = peers->rank;
+    for (int g = 0; g < peers->n_ranks; ++g)
+      push.dst[g] = reinterpret_cast<int2*>(reinterpret_cast<uint8_t*>(peers->base[g]) + peer_gather_offset);
+  }
   EVAVOS_CUDA_OK(launch_pdl(finalize_kernel, dim3((unsigned)ceil_div(n_query, kFinWarps)), dim3(32 * kFinWarps), 0, st,
                             key_pm, query, query_ch_stride, CK, n_pos, n_query, top_k, cand, cand_cnt, scored,
-                            key_maxnorm, out_idx, out_weight, out_score));
+                            key_maxnorm, out_idx, out_weight, out_score, push));
   return EVAVOS_OK;
 }
 

@@ -75,13 +75,16 @@ def _require_cuda(t: torch.Tensor, name: str):
 
 def memory_read(bank: MemoryBank, qk: torch.Tensor, top_k: int = 50, n_frames: int | None = None,
                 want_readout: bool = True, want_topk: bool = False, path: int = _lib.PATH_AUTO,
-                sample_stride: int | None = None, out: torch.Tensor | None = None):
+                sample_stride: int | None = None, out: torch.Tensor | None = None, peers=None,
+                peer_gather_offset: int = 0):
     """Fused read of ``qk`` (1,CK,H,W) or (1,CK,F,H,W) against the first ``n_frames`` of ``bank``.
 
     ``sample_stride`` (tensor path): the filter's threshold pass contracts every sample_stride-th key tile
     (None/0: the library's choice, or $EVAVOS_SAMPLE_STRIDE when set - a tuning knob, results do not depend on it).
     ``out``: optional pre-allocated fp32 destination viewed as (K, >=CV, nq) - e.g. the first CV channels of the
     decoder's (K, 2*CV, H, W) input, so that no torch.cat is needed (prop_net.py:189-190).
+    ``peers`` (an ``_lib.Peers``) / ``peer_gather_offset``: sharded read - the finalizer also stores every query's
+    list into all ranks' exchange buffers (see include/evavos.h, EvavosMemReadArgs.peers).
     Returns (readout (K,CV,[F,]H,W) or None, TopKAffinity or None).
     """
     lib = _lib.load()
@@ -103,6 +106,9 @@ def memory_read(bank: MemoryBank, qk: torch.Tensor, top_k: int = 50, n_frames: i
     a.query_ch_stride = q2.stride(0)
     a.n_pos, a.n_query, a.top_k, a.path = n_pos, nq, int(top_k), int(path)
     a.sample_stride = int(sample_stride if sample_stride else os.environ.get("EVAVOS_SAMPLE_STRIDE", 0))
+    if peers is not None:
+        a.peers = ctypes.pointer(peers)
+        a.peer_gather_offset = int(peer_gather_offset)
     idx = weight = score = None
     user_out = out
     if want_readout:

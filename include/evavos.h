@@ -21,8 +21,12 @@
  *   evavos_attention_readout replaces AttentionMemory.forward + the two vector-matrix products of
  *                           get_attention (mivos/model/propagation/prop_net.py:117-138, 204-207) without
  *                           materialising the (HW, HW) softmax matrix.
+ *   evavos_jf_metrics       replaces the per-frame J / J&F scoring of interactions/eval.py:27-81 and
+ *                           interactions/metrics.py:9-160.
  *   evavos_topk_merge       the exchange step of the memory-axis sharded read
- *                           (no reference counterpart).
+ *                           (no reference counterpart); evavos_peer_barrier,
+ *                           evavos_peer_reduce_scatter and the `peers` field of the read move its data over
+ *                           NVLink peer memory from inside the kernels.
  *   evavos_memread_host     the same read with HOST buffers in the reference layout
  *                           (what a ctypes/cgo caller without device memory would bind).
  *
@@ -64,7 +68,7 @@
 extern "C" {
 #endif
 
-#define EVAVOS_ABI_VERSION 1
+#define EVAVOS_ABI_VERSION 2
 
 #define EVAVOS_OK 0
 #define EVAVOS_ERR_INVALID (-1)     /* bad argument (null pointer, non-positive size, ...) */
@@ -99,6 +103,20 @@ typedef struct EvavosBankShadow {
   int32_t val_dtype;   /* EVAVOS_F32 | EVAVOS_BF16                                   */
 } EvavosBankShadow;
 
+#define EVAVOS_MAX_RANKS 16
+
+/*
+ * Exchange buffers of the ranks of a memory-axis sharded bank (one process per GPU): base[g] is rank g's buffer as
+ * mapped into THIS process (CUDA IPC / peer access over NVLink; base[rank] is the local one).  The kernels below
+ * store to and load from these pointers directly - the exchange steps of the sharded read are device-initiated,
+ * no host-side collective is on the data path.
+ */
+typedef struct EvavosPeers {
+  int32_t n_ranks;
+  int32_t rank;
+  void* base[EVAVOS_MAX_RANKS];
+} EvavosPeers;
+
 /* Arguments of the fused read. */
 typedef struct EvavosMemReadArgs {
   EvavosBankShadow bank;
@@ -119,6 +137,12 @@ typedef struct EvavosMemReadArgs {
   int32_t n_sm;            /* SM count to size grids for (0 -> query the device)      */
   int32_t sample_stride;   /* tensor path: the threshold pass contracts every sample_stride-th key tile
                               (0 -> the library's choice; 1 = two full sweeps; clamped for short banks) */
+  /* Sharded read (optional, NULL otherwise): the finalizer also stores this rank's per-query list as packed
+     (LOCAL position or -1, score bits) int32 pairs into EVERY rank's buffer at byte offset peer_gather_offset,
+     laid out [n_ranks][n_query][top_k][2] with this rank's rows in slot `rank` - the all-gather of the sharded
+     read, done by the epilogue of the kernel that produces the lists (evavos_topk_merge_gathered consumes it). */
+  const EvavosPeers* peers;
+  int64_t peer_gather_offset;
 } EvavosMemReadArgs;
 
 int evavos_abi_version(void);
@@ -177,6 +201,19 @@ int evavos_argmax_unpad(const float* prob, int32_t C, int64_t T, int32_t nh, int
                         int32_t pad_top, int32_t pad_left, int32_t h, int32_t w, evavos_stream_t stream);
 
 /*
+ * Per-frame segmentation quality of a whole video on the device (replaces the per-frame numpy + cv2 loop of
+ * interactions/eval.py:27-81 -> interactions/metrics.py:9-36, 40-160).  pred, gt: (T, h, w) uint8, non-zero =
+ * foreground.  bound_pix = ceil(0.008 * sqrt(h^2 + w^2)) in the reference (metrics.py:120-121), at most 24.
+ *   out (T, 4) fp64: smoothed IoU `compute_iou`, binary Jaccard, boundary F-measure, 0.5 * Jaccard + 0.5 * F
+ *   gt_empty (T) int32, optional: 1 where the ground truth has no foreground pixel (eval.py:60-63 skips those)
+ * workspace: evavos_jf_workspace_bytes() bytes.
+ */
+size_t evavos_jf_workspace_bytes(int64_t T, int32_t h, int32_t w);
+int evavos_jf_metrics(const uint8_t* pred, const uint8_t* gt, int64_t T, int32_t h, int32_t w, int32_t bound_pix,
+                      void* workspace, int64_t workspace_bytes, double* out, int32_t* gt_empty,
+                      evavos_stream_t stream);
+
+/*
  * Full-softmax attention read of ONE memory frame (the fusion path, prop_net.py:117-138 and :204-207):
  *   out[c][q] = sum_n vec[c][n] * softmax_n((-|m_n|^2 + 2 m_n.q_q - |q_q|^2) / sqrt(CK))
  * mem_key (CK, n_mem) and query_key (CK, n_query) fp32 with the given channel strides, unit position stride;
@@ -213,6 +250,31 @@ int evavos_topk_merge(const int32_t* cand_idx, const float* cand_score, int64_t 
 int evavos_topk_merge_gathered(const int32_t* gathered, int64_t n_query, int32_t per_shard, int32_t top_k,
                                int32_t shard, int32_t n_shards, int64_t pos_per_frame, int32_t* out_idx,
                                float* out_weight, float* out_score, int32_t* local_idx, evavos_stream_t stream);
+
+/*
+ * Sparse readout in query-major form: out (n_query, K, CV) fp32, one contiguous row per query (the layout the
+ * sharded read sums over ranks: a slice of queries is a contiguous chunk).
+ */
+int evavos_readout_qmajor(const EvavosBankShadow* bank, const int32_t* idx, const float* weight, int64_t n_query,
+                          int32_t top_k, float* out, evavos_stream_t stream);
+
+/*
+ * Barrier among the ranks of `peers`, on the device: every rank stores `epoch` into its slot of every peer's flag
+ * array (32 x uint32 at byte offset flag_offset of each buffer, zero-initialised; epochs must increase by one per
+ * call on every rank) and waits until all peers' epochs have arrived in its own.  Orders everything the stream did
+ * before the call (stores to peer buffers included) before everything after it on all ranks.  A peer that does not
+ * show up within ~2 s makes the kernel give up and poison slot 31 (checked by evavos_peer_barrier_ok).
+ */
+int evavos_peer_barrier(const EvavosPeers* peers, int64_t flag_offset, uint32_t epoch, evavos_stream_t stream);
+
+/*
+ * Sum-reduce-scatter over peer memory: out[row][q - q0] = sum_g partial_g[q][row] for q in [q0, q1), where
+ * partial_g = (n_query, rows) fp32 query-major at byte offset partial_offset of rank g's buffer (rows = K * CV,
+ * written by evavos_readout_qmajor).  out is (rows, q1 - q0) fp32 with row stride out_row_stride - the slice of
+ * the reference-layout readout (K, CV, HW) this rank owns.  Loads come straight from the peers' memory.
+ */
+int evavos_peer_reduce_scatter(const EvavosPeers* peers, int64_t partial_offset, int32_t rows, int64_t q0,
+                               int64_t q1, float* out, int64_t out_row_stride, evavos_stream_t stream);
 
 /*
  * Host-buffer form of the read, reference layouts, synchronous:

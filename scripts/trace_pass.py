@@ -47,7 +47,7 @@ lib.evavos_debug_trace.argtypes = [ctypes.c_void_p]
 print("rc", lib.evavos_debug_trace(buf))
 tr = np.array(list(buf), dtype=np.int64).reshape(6, 64)
 t0 = tr[1, 0] if i0 == 0 else tr[0, 57]
-names = ["prod_issue", "mma_ready", "mma_issued", "epi_accfull", "epi_ldtm_done", "epi_math_done"]
+names = ["full_ready", "mma_ready", "mma_issued", "epi_accfull", "epi_ldtm_done", "epi_math_done"]
 print("tile " + " ".join(f"{n:>13s}" for n in names))
 for i in range(0, 40):
     print(f"{i:4d} " + " ".join(f"{int(tr[r, i] - t0):13d}" for r in range(6)))
@@ -55,5 +55,6 @@ print("kernel marks (entry, roles start, end sweep2, exit):", [int(x - t0) for x
 print("phase marks (end phase A, after barrier1, after thresholds, after barrier2):", [int(x - t0) for x in tr[0, 60:64]])
 d = np.diff(tr[:, 8:40], axis=1)
 print("mean cycles/tile (tiles 8..40):", {n: float(d[r].mean()) for r, n in enumerate(names)})
+print("issued(i-1) -> full_ready(i)", float((tr[0, 9:40] - tr[2, 8:39]).mean()), " full_ready -> mma_ready (wait for acc_empty)", float((tr[1, 8:40] - tr[0, 8:40]).mean()))
 print("mma_ready -> issued", float((tr[2, 8:40] - tr[1, 8:40]).mean()), " accfull -> ldtm", float((tr[4, 8:40] - tr[3, 8:40]).mean()),
       " ldtm -> math", float((tr[5, 8:40] - tr[4, 8:40]).mean()), " issued(i) -> accfull(i)", float((tr[3, 8:40] - tr[2, 8:40]).mean()))

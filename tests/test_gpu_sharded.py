@@ -43,6 +43,7 @@ def test_two_shards_on_one_device_equal_single_bank():
         assert (gidx == aff.idx).all()
         assert (w - aff.weight).abs().max() < 1e-6
         owned = (loc >= 0).sum(1)
+    total = total.permute(1, 2, 0).contiguous()          # the partial readouts are query-major (nq, K, CV)
     assert (total.view_as(ref) - ref).abs().max() < 1e-5
     assert int(owned.max()) <= top_k
     # the packed all-gather layout [shard][query][k][2] gives the same merge
@@ -54,50 +55,80 @@ def test_two_shards_on_one_device_equal_single_bank():
         assert (gidx2 == aff.idx).all() and (w2 - aff.weight).abs().max() < 1e-6
         part = ops.readout(b, loc2, w2)
         total2 = part if total2 is None else total2 + part
-    assert torch.equal(total2, total)
+    assert torch.equal(total2.permute(1, 2, 0).contiguous(), total)
     # against the oracle too
     tk, ro = onp.memory_read(mk[0].reshape(CK, -1).numpy(), qk[0].reshape(CK, -1).numpy(), mv.reshape(K, CV, -1).numpy(), top_k)
     assert onp.rel_l2(total.cpu().numpy().reshape(ro.shape), ro) < 1e-5
 
 
-def _nccl_worker(rank, world, port, ret):
+def _sharded_worker(rank, world, port, ret, backend, same_device):
+    """One rank of a sharded read.  backend "nccl": one GPU per rank, both exchange engines.  backend "gloo" with
+    same_device: all ranks share cuda:0 (CUDA IPC works between processes on one device) - the peer-memory engine
+    needs no NCCL at all, only a process group to pass the IPC handles, so it can be checked on a 1-GPU box."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     import torch.distributed as dist
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dev = torch.device("cuda", 0 if same_device else rank)
+    torch.cuda.set_device(dev)
+    if backend == "nccl":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        import evavos_b200 as ev
-        from evavos_b200.sharded import ShardedMemoryBank
-        dev = torch.device("cuda", rank)
-        K, CK, CV, T, H, W = 1, 64, 512, 9, 12, 16
-        mk, qk, mv = synth(17, CK, CV, T, H, W, K)
-        bank = ShardedMemoryBank(K, CK, CV, H, W, T, dev)
-        for f in range(T):
-            bank.append(mk[:, :, f].to(dev), mv[:, :, f:f + 1].to(dev))
-        out = bank.read(qk.to(dev), 50)
-        torch.cuda.synchronize()
+        from evavos_b200.sharded import ShardedMemoryBank, query_slice
+        K, CK, CV, T, H, W = 2, 64, 512, 9, 12, 16
+        mk, _, mv = synth(17, CK, CV, T, H, W, K)
+        qk = torch.randn(1, CK, 3, H, W, generator=torch.Generator().manual_seed(18))     # 3 query frames, 576 queries
         tk, ro = onp.memory_read(mk[0].reshape(CK, -1).numpy(), qk[0].reshape(CK, -1).numpy(), mv.reshape(K, CV, -1).numpy(), 50)
-        err = onp.rel_l2(out.cpu().numpy().reshape(ro.shape), ro)
-        assert err < 1e-5, err
+        engines = ["peer", "nccl"] if backend == "nccl" else ["peer"]
+        for engine in engines:
+            bank = ShardedMemoryBank(K, CK, CV, H, W, T, dev, exchange=engine)
+            for f in range(T):
+                bank.append(mk[:, :, f].to(dev), mv[:, :, f:f + 1].to(dev))
+            for rep in range(3):      # several reads through the same exchange buffers (barrier epochs, buffer reuse)
+                mine, gidx, w = bank.read(qk.to(dev), 50, return_topk=True, scatter=True)
+                torch.cuda.synchronize()
+                q0, q1 = query_slice(3 * H * W, rank, world)
+                assert mine.shape == (K, CV, q1 - q0)
+                assert (gidx.cpu().numpy() == tk.idx).all(), engine
+                assert np.abs(w.cpu().numpy() - tk.weight).max() < 1e-6
+                err = onp.rel_l2(mine.cpu().numpy(), ro[:, :, q0:q1])
+                assert err < 1e-5, (engine, rep, err)
+            if bank._peer is not None:
+                assert bank._peer.ok(), "a peer barrier timed out"
+            if backend == "nccl":      # replicated form (all-gather of the slices)
+                out = bank.read(qk.to(dev), 50)
+                assert onp.rel_l2(out.cpu().numpy().reshape(ro.shape), ro) < 1e-5
         ret[rank] = True
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_sharded_read_over_nccl():
+def _run_ranks(world, backend, same_device):
     import torch.multiprocessing as mp
-    world = 2
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, ret)) for r in range(world)]
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, ret, backend, same_device)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(300)
+        if p.is_alive():
+            p.terminate()
         assert p.exitcode == 0
     assert all(ret.get(r) for r in range(world))
+
+
+def test_peer_memory_exchange_two_ranks_on_one_gpu():
+    """The device-initiated exchange (finalizer push over IPC-mapped peer buffers, device-side barriers, reduce-scatter
+    by peer loads) with two processes sharing cuda:0: no NCCL involved, so it runs on the driver's 1-GPU box."""
+    _run_ranks(2, "gloo", True)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_read_over_nvlink_two_gpus():
+    """Both exchange engines (peer memory, NCCL) with one GPU per rank."""
+    _run_ranks(2, "nccl", False)

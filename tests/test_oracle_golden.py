@@ -116,3 +116,20 @@ def test_oracle_attention(name):
                        torch.nn.functional.interpolate(neg, size=(nh, nw), mode="area").view(b, -1)], 1)
     o64 = onp.attention_readout(mk.reshape(64, -1).numpy(), qk.reshape(64, -1).numpy(), vec.reshape(2 * b, -1).numpy())
     assert np.abs(o64.reshape(b, 2, nh, nw) - low.numpy()).max() < 2e-6
+
+
+def test_jf_restatement_reproduces_reference_metrics():
+    """oracle/jf_np.py against tests/golden/jf.npz (written by the reference's own interactions/metrics.py)."""
+    from oracle import jf_np
+    g = load("jf.npz")
+    for name in ("small", "odd"):
+        shape = tuple(int(x) for x in g[f"{name}_shape"])
+        pred = np.unpackbits(g[f"{name}_pred"], axis=-1)[..., :shape[2]].astype(bool)
+        gt = np.unpackbits(g[f"{name}_gt"], axis=-1)[..., :shape[2]].astype(bool)
+        for f in range(shape[0]):
+            assert jf_np.compute_iou(pred[f], gt[f]) == g[f"{name}_j"][f]
+            if gt[f].any():
+                assert jf_np.j_and_f(pred[f], gt[f]) == g[f"{name}_jf"][f]
+                assert jf_np.f_measure(pred[f], gt[f]) == g[f"{name}_f"][f]
+            else:
+                assert g[f"{name}_jf"][f] == 20

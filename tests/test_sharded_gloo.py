@@ -60,8 +60,8 @@ class _OracleOps:
     def readout(self, bank, local_idx, weight):
         li, w = local_idx.numpy().astype(np.int64), weight.numpy().astype(np.float64)
         w = np.where(li >= 0, w, 0.0)
-        out = onp.readout(np.maximum(li, 0), w, bank.vals[:, :, :max(bank.n_pos, 1)])
-        return torch.from_numpy(out.astype(np.float32))
+        out = onp.readout(np.maximum(li, 0), w, bank.vals[:, :, :max(bank.n_pos, 1)])       # (K, CV, nq)
+        return torch.from_numpy(np.ascontiguousarray(out.transpose(2, 0, 1)).astype(np.float32))  # query-major
 
 
 def _free_port():
@@ -92,6 +92,12 @@ def _worker(rank, world, port, frames, top_k, ret):
         assert (gidx.numpy() == tk.idx).all(), "merged global top-k differs from the single-bank oracle"
         assert np.abs(w.numpy() - tk.weight).max() < 1e-6
         assert np.abs(out.reshape(K, CV, -1).numpy() - ro).max() < 1e-5
+        # scattered form: every rank keeps the query slice it owns
+        from evavos_b200.sharded import query_slice
+        mine = bank.read(qk, top_k, scatter=True)
+        q0, q1 = query_slice(2 * H * W, rank, world)
+        assert mine.shape == (K, CV, q1 - q0)
+        assert np.abs(mine.numpy() - ro[:, :, q0:q1]).max() < 1e-5
         # index mapping round trip
         loc = torch.arange(bank.local.n_pos, dtype=torch.int32)
         glob = local_to_global(loc, rank, world, H * W)
