@@ -51,6 +51,7 @@ class MemReadArgs(ctypes.Structure):
         ("readout_obj_stride", _c_i64), ("readout_ch_stride", _c_i64),
         ("top_k", _c_i32), ("path", _c_i32), ("n_sm", _c_i32), ("sample_stride", _c_i32),
         ("peers", ctypes.POINTER(Peers)), ("peer_gather_offset", _c_i64),
+        ("queries_per_frame", _c_i64), ("readout_frame_stride", _c_i64),
     ]
 
 

@@ -63,7 +63,7 @@ struct Carve {
 Carve carve_workspace(const EvavosMemReadArgs& a, int n_chunks, int n_sm, uint8_t* base) {
   Carve c;
   memset(&c, 0, sizeof(c));
-  const int64_t mt = ceil_div(a.n_query, 128);
+  const int64_t mt = score_pass_mtiles(a.n_query);   // whole clusters of query tiles (select buffers cover the padding)
   const int64_t nq_pad = mt * 128;
   size_t off = 0;
   auto take = [&](size_t bytes) -> uint8_t* {
@@ -129,6 +129,11 @@ int validate_read(const EvavosMemReadArgs* a) {
     return EVAVOS_ERR_UNSUPPORTED;
   }
   if (a->readout && (!a->bank.val_pm || a->bank.K <= 0)) { set_error("readout requested without values"); return EVAVOS_ERR_INVALID; }
+  if (a->queries_per_frame < 0 || a->queries_per_frame > 0x7fffffff ||
+      (a->queries_per_frame > 0 && (a->n_query % a->queries_per_frame) != 0)) {
+    set_error("queries_per_frame must divide n_query");
+    return EVAVOS_ERR_INVALID;
+  }
   if (a->peers != nullptr) {
     int rc2 = validate_peers(a->peers);
     if (rc2) return rc2;
@@ -268,7 +273,7 @@ int evavos_memread(const EvavosMemReadArgs* a, evavos_stream_t stream) {
   // 1. candidate generation (the query is consumed in the caller's layout; no query shadow)
   stage_mark(0, st);
   if (tensor) {
-    const int stride = score_pass_sample_stride(a->n_pos, a->sample_stride);
+    const int stride = score_pass_sample_stride(a->n_pos, chunks, a->sample_stride);
     rc = launch_score_select(a->query, a->query_ch_stride, a->bank.key_tiles, a->bank.key_maxnorm, a->n_pos, a->n_query,
                              a->top_k, chunks, stride, n_sm, c.sb.class_max, c.sb.tau, c.sb.cand, c.sb.cand_cnt,
                              c.sb.strip, c.sb.grid_counter, st);
@@ -291,7 +296,7 @@ int evavos_memread(const EvavosMemReadArgs* a, evavos_stream_t stream) {
   // 3. sparse readout for all objects
   if (a->readout) {
     rc = launch_readout(a->bank, idx, weight, a->n_query, a->top_k, a->readout, a->readout_obj_stride,
-                        a->readout_ch_stride, st);
+                        a->readout_ch_stride, (int)a->queries_per_frame, a->readout_frame_stride, st);
     if (rc) return rc;
   }
   stage_mark(4, st);
@@ -308,7 +313,7 @@ int evavos_readout(const EvavosBankShadow* bank, const int32_t* idx, const float
     set_error("readout: bad arguments");
     return EVAVOS_ERR_INVALID;
   }
-  return launch_readout(*bank, idx, weight, n_query, top_k, out, out_obj_stride, out_ch_stride, (cudaStream_t)stream);
+  return launch_readout(*bank, idx, weight, n_query, top_k, out, out_obj_stride, out_ch_stride, 0, 0, (cudaStream_t)stream);
 }
 
 int evavos_readout_qmajor(const EvavosBankShadow* bank, const int32_t* idx, const float* weight, int64_t n_query,
@@ -320,7 +325,7 @@ int evavos_readout_qmajor(const EvavosBankShadow* bank, const int32_t* idx, cons
     set_error("readout_qmajor: bad arguments");
     return EVAVOS_ERR_INVALID;
   }
-  return launch_readout(*bank, idx, weight, n_query, top_k, out, 0, -1, (cudaStream_t)stream);
+  return launch_readout(*bank, idx, weight, n_query, top_k, out, 0, -1, 0, 0, (cudaStream_t)stream);
 }
 
 int evavos_peer_barrier(const EvavosPeers* peers, int64_t flag_offset, uint32_t epoch, evavos_stream_t stream) {

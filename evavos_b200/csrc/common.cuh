@@ -138,10 +138,12 @@ int launch_score_select(const float* query, int64_t query_ch_stride, const void*
                         unsigned int* grid_counter, cudaStream_t st);
 size_t score_pass_strip_bytes(int64_t n_query, int n_chunks, int n_sm);
 int score_pass_chunks(int64_t n_pos, int64_t n_query, int n_sm);
-int score_pass_sample_stride(int64_t n_pos, int requested);
+int64_t score_pass_mtiles(int64_t n_query);
+int score_pass_sample_stride(int64_t n_pos, int n_chunks, int requested);
 
 int launch_readout(const EvavosBankShadow& b, const int32_t* idx, const float* weight, int64_t n_query,
-                   int top_k, float* out, int64_t out_obj_stride, int64_t out_ch_stride, cudaStream_t st);
+                   int top_k, float* out, int64_t out_obj_stride, int64_t out_ch_stride, int q_per_frame,
+                   int64_t frame_stride, cudaStream_t st);
 int launch_affinity_dense(const int32_t* idx, const float* weight, int64_t n_query, int top_k, int64_t n_pos,
                           float* dense, cudaStream_t st);
 int launch_aggregate(const float* prob, float* out, int K, int64_t npix, int keep_bg, int hard,

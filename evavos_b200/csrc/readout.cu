@@ -18,6 +18,14 @@ constexpr int kQPerCta = 8;  // one warp per query
 constexpr int kRowUnroll = 5;
 __device__ __forceinline__ float4 ld_row(const float4* p) { return __ldg(p); }
 
+// Where query q lands inside a (object, channel) row: plain q, or - when several query frames are read in one launch
+// and every frame has its own destination block (the decoder input (F, K, 2*CV, H, W)) - frame * frame_stride + position.
+__device__ __forceinline__ int64_t query_offset(int64_t q, int q_per_frame, int64_t frame_stride) {
+  if (q_per_frame <= 0) return q;
+  const uint32_t f = (uint32_t)q / (uint32_t)q_per_frame;
+  return (int64_t)f * frame_stride + (int64_t)((uint32_t)q - f * (uint32_t)q_per_frame);
+}
+
 __device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
   a.x = fmaf(w, v.x, a.x);
   a.y = fmaf(w, v.y, a.y);
@@ -33,7 +41,7 @@ template <int NV, bool QMAJOR>
 __global__ void __launch_bounds__(256) readout_f32_kernel(
     const float* __restrict__ val_pm_all, int64_t capacity_pos, int CVfull, const int32_t* __restrict__ idx,
     const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out_all,
-    int64_t out_obj_stride, int64_t out_ch_stride) {
+    int64_t out_obj_stride, int64_t out_ch_stride, int q_per_frame, int64_t frame_stride) {
   pdl_wait();  // idx / weight come from the kernel before (programmatic dependent launch)
   pdl_launch_dependents();
   constexpr int CV = 128 * NV;
@@ -85,7 +93,8 @@ __global__ void __launch_bounds__(256) readout_f32_kernel(
   const int nq_here = (int)min((int64_t)kQPerCta, n_query - q0);
   for (int e = threadIdx.x; e < CV * kQPerCta; e += 256) {
     const int c = e / kQPerCta, w = e % kQPerCta;
-    if (w < nq_here) out[(int64_t)o * out_obj_stride + (int64_t)c * out_ch_stride + q0 + w] = st[c][w];
+    if (w < nq_here)
+      out[(int64_t)o * out_obj_stride + (int64_t)c * out_ch_stride + query_offset(q0 + w, q_per_frame, frame_stride)] = st[c][w];
   }
 }
 
@@ -94,7 +103,7 @@ template <int NV, bool QMAJOR>
 __global__ void __launch_bounds__(256) readout_bf16_kernel(
     const __nv_bfloat16* __restrict__ val_pm, int64_t capacity_pos, const int32_t* __restrict__ idx,
     const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out,
-    int64_t out_obj_stride, int64_t out_ch_stride) {
+    int64_t out_obj_stride, int64_t out_ch_stride, int q_per_frame, int64_t frame_stride) {
   pdl_wait();  // idx / weight come from the kernel before (programmatic dependent launch)
   pdl_launch_dependents();
   constexpr int CV = 256 * NV;
@@ -153,7 +162,8 @@ __global__ void __launch_bounds__(256) readout_bf16_kernel(
   const int nq_here = (int)min((int64_t)kQPerCta, n_query - q0);
   for (int e = threadIdx.x; e < CV * kQPerCta; e += 256) {
     const int c = e / kQPerCta, w = e % kQPerCta;
-    if (w < nq_here) out[(int64_t)o * out_obj_stride + (int64_t)c * out_ch_stride + q0 + w] = st[c][w];
+    if (w < nq_here)
+      out[(int64_t)o * out_obj_stride + (int64_t)c * out_ch_stride + query_offset(q0 + w, q_per_frame, frame_stride)] = st[c][w];
   }
 }
 
@@ -162,7 +172,7 @@ template <typename VT>
 __global__ void __launch_bounds__(128) readout_generic_kernel(
     const VT* __restrict__ val_pm, int64_t capacity_pos, int CV, const int32_t* __restrict__ idx,
     const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out,
-    int64_t out_obj_stride, int64_t out_ch_stride) {
+    int64_t out_obj_stride, int64_t out_ch_stride, int q_per_frame, int64_t frame_stride) {
   pdl_wait();  // idx / weight come from the kernel before (programmatic dependent launch)
   pdl_launch_dependents();
   __shared__ int32_t s_n[EVAVOS_MAX_TOPK];
@@ -186,7 +196,7 @@ __global__ void __launch_bounds__(128) readout_generic_kernel(
       acc = fmaf(s_w[j], v, acc);
     }
     if (out_ch_stride < 0) out[((int64_t)q * gridDim.y + o) * CV + c] = acc;   // query-major (see launch_readout)
-    else out[(int64_t)o * out_obj_stride + (int64_t)c * out_ch_stride + q] = acc;
+    else out[(int64_t)o * out_obj_stride + (int64_t)c * out_ch_stride + query_offset(q, q_per_frame, frame_stride)] = acc;
   }
 }
 
@@ -203,7 +213,8 @@ __global__ void scatter_dense_kernel(const int32_t* __restrict__ idx, const floa
 
 // out_ch_stride < 0 selects the query-major output (n_query, K, CV).
 int launch_readout(const EvavosBankShadow& b, const int32_t* idx, const float* weight, int64_t n_query,
-                   int top_k, float* out, int64_t out_obj_stride, int64_t out_ch_stride, cudaStream_t st) {
+                   int top_k, float* out, int64_t out_obj_stride, int64_t out_ch_stride, int q_per_frame,
+                   int64_t frame_stride, cudaStream_t st) {
   if (n_query <= 0) return EVAVOS_OK;
   const bool qmajor = out_ch_stride < 0;
   if (out_ch_stride == 0) out_ch_stride = n_query;
@@ -213,12 +224,12 @@ int launch_readout(const EvavosBankShadow& b, const int32_t* idx, const float* w
 #define EVAVOS_RO_F32_(NV, SPLIT, QM)                                                                         \
   EVAVOS_CUDA_OK(launch_pdl(readout_f32_kernel<NV, QM>, dim3(grid.x, grid.y, SPLIT), dim3(256), 0, st,        \
                             reinterpret_cast<const float*>(b.val_pm), b.capacity_pos, b.CV, idx, weight,      \
-                            n_query, top_k, out, out_obj_stride, out_ch_stride))
+                            n_query, top_k, out, out_obj_stride, out_ch_stride, q_per_frame, frame_stride))
 #define EVAVOS_RO_F32(NV, SPLIT) do { if (qmajor) EVAVOS_RO_F32_(NV, SPLIT, true); else EVAVOS_RO_F32_(NV, SPLIT, false); } while (0)
 #define EVAVOS_RO_BF16_(NV, QM)                                                                               \
   EVAVOS_CUDA_OK(launch_pdl(readout_bf16_kernel<NV, QM>, grid, dim3(256), 0, st,                              \
                             reinterpret_cast<const __nv_bfloat16*>(b.val_pm), b.capacity_pos, idx, weight,    \
-                            n_query, top_k, out, out_obj_stride, out_ch_stride))
+                            n_query, top_k, out, out_obj_stride, out_ch_stride, q_per_frame, frame_stride))
 #define EVAVOS_RO_BF16(NV) do { if (qmajor) EVAVOS_RO_BF16_(NV, true); else EVAVOS_RO_BF16_(NV, false); } while (0)
   if (b.val_dtype == EVAVOS_F32 && row16 && b.CV % 128 == 0 && b.CV <= 512) {
     // Splitting a row's channels over two CTAs (more resident warps) was measured SLOWER on B200 (55 vs 42 us at
@@ -238,11 +249,11 @@ int launch_readout(const EvavosBankShadow& b, const int32_t* idx, const float* w
     if (b.val_dtype == EVAVOS_BF16)
       readout_generic_kernel<__nv_bfloat16><<<g2, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(b.val_pm),
                                                                 b.capacity_pos, b.CV, idx, weight, n_query, top_k,
-                                                                out, out_obj_stride, out_ch_stride);
+                                                                out, out_obj_stride, out_ch_stride, q_per_frame, frame_stride);
     else
       readout_generic_kernel<float><<<g2, 128, 0, st>>>(reinterpret_cast<const float*>(b.val_pm), b.capacity_pos,
                                                         b.CV, idx, weight, n_query, top_k, out, out_obj_stride,
-                                                        out_ch_stride);
+                                                        out_ch_stride, q_per_frame, frame_stride);
   }
 #undef EVAVOS_RO_F32
 #undef EVAVOS_RO_F32_

@@ -44,7 +44,9 @@ __device__ int g_trace_i0 = 0;
 
 // Compile-time timing experiments (-DEVAVOS_EXP=bits; results are wrong while a bit is set):
 // 1 = the epilogue skips the TMEM load, 2 = skips its math, 4 = the producers copy only 4 KB of every tile image
-// (is the L2 -> shared-memory path the bound?), 8 = phase B never takes the hit path (cost of staging).
+// (is the L2 -> shared-memory path the bound?), 8 = phase B never takes the hit path (cost of staging),
+// 16 = the MMA issuer does not wait for the key tile to land (is the TMA ring the bound?), 32 = the epilogue hands
+// the accumulator stage back before it has read it (is the stage hand-off the bound?).
 #ifndef EVAVOS_EXP
 #define EVAVOS_EXP 0
 #endif
@@ -57,6 +59,17 @@ namespace {
 #ifndef EVAVOS_PRODUCERS
 #define EVAVOS_PRODUCERS 4
 #endif
+// EVAVOS_CLUSTER = 2: the CTAs of two neighbouring query tiles (same memory chunk) form a cluster and share every
+// key tile - each CTA fetches HALF of the 20 KB tile image and multicasts it into both CTAs' shared memory, which
+// halves the L2 -> SM traffic.  (Measured in round 2: with every CTA pulling every tile the chip moves
+// 148 x 20 KB per ~500 clk = 5.9 KB/clk out of L2, right at the ~6.3 KB/clk the L2 can deliver - the threshold pass
+// was L2-bandwidth-bound.)  The MMAs stay cta_group::1; only the smem ring is coupled: a stage may be refilled
+// when BOTH CTAs' MMAs have read it (the `empty` barrier counts a multicast commit from each CTA).
+#ifndef EVAVOS_CLUSTER
+#define EVAVOS_CLUSTER 1
+#endif
+constexpr int kCluster = EVAVOS_CLUSTER;
+static_assert(kCluster == 1 || kCluster == 2, "clusters of 1 or 2 CTAs");
 constexpr int kStages = EVAVOS_STAGES;
 constexpr int kAccStages = 3;   // 3 x 128 accumulator columns; the query operand lives in columns [384, 424)
 constexpr int kQueryCol = 384;
@@ -74,7 +87,7 @@ constexpr int kWarpProducer = 16, kWarpIssuer = 17, kWarpAlloc = 19;   // warps 
 constexpr int kEpiLeader = 0;   // thread that runs the grid barrier / trace marks of the epilogue
 constexpr int kCols = 32;       // accumulator columns per tcgen05.ld
 constexpr int kClasses = 128;   // column classes per query and chunk (phase A)
-constexpr int kStrip = 16;      // staged 8-score groups per epilogue thread before they are resolved into the list
+constexpr int kStrip = 24;      // staged 8-score groups per epilogue thread before they are resolved into the list
 constexpr int kBarBytes = 256;
 constexpr int kSmemBytes = kTileBytes * kStages + kBarBytes + 1024;
 constexpr uint32_t kCopyBytes = (EVAVOS_EXP & 4) ? 4096 : kTileBytes;   // bytes the producers move per tile image
@@ -126,6 +139,22 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// Half a tile image, written to the same offset of BOTH CTAs of the cluster; completes bytes on both `full` barriers.
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // One lane of a converged warp (the tcgen05 issue idiom: the branch stays warp-uniform for the compiler).
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -152,6 +181,12 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// the same arrive on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 
 // K-major operand descriptors (16-byte units; version 1 = Blackwell).
@@ -231,25 +266,64 @@ struct PassParams {
 // with all lanes busy instead of a stall per tile.  For the same reason the hot path stays free of calls and of
 // per-hit bookkeeping: the visit time of a group is the MAXIMUM over its 8 warps, so every cycle of a rare path
 // that some warp takes on most visits is paid on most visits.
-__device__ __noinline__ void flush_strip(const float4* ss, const int32_t* sp, int n, bool overflow, float thr,
-                                         int2* cand, int32_t* cand_cnt, int64_t q) {
-  int hits = overflow ? kCandCap + 1 : 0;
-  for (int e = 0; e < 2 * n; ++e) {
-    const float4 s = ss[(int64_t)e * kEpiThreads];
-    hits += (s.x >= thr) + (s.y >= thr) + (s.z >= thr) + (s.w >= thr);
+// The strip lives in global memory (L2): every access is a ~700-1000 clk round trip, so the entries are pulled in
+// batches of 4 groups with all 12 loads of a batch in flight together (a first version walked the strip entry by
+// entry - two dependent round trips per group and pass, ~20 000 clk per call, which WAS the candidate pass of a
+// short bank like cfg2).  A strip of up to 4 groups (the common case) is read once: count, reserve, copy out of
+// registers.
+struct StripBatch {
+  float4 s[8];
+  int32_t pos[4];
+};
+__device__ __forceinline__ void strip_load(StripBatch& b, const float4* ss, const int32_t* sp, int g0, int n) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const bool live = g0 + g < n;
+    b.s[2 * g] = live ? ss[(int64_t)(2 * (g0 + g)) * kEpiThreads] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    b.s[2 * g + 1] = live ? ss[(int64_t)(2 * (g0 + g) + 1) * kEpiThreads] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    b.pos[g] = live ? sp[(int64_t)(g0 + g) * kEpiThreads] : 0;
   }
-  int at = atomicAdd(cand_cnt + q, hits);
-  for (int e = 0; e < 2 * n; ++e) {
-    const float4 s = ss[(int64_t)e * kEpiThreads];
-    const int32_t n0 = sp[(int64_t)(e >> 1) * kEpiThreads] + 4 * (e & 1);
-    const float v[4] = {s.x, s.y, s.z, s.w};
+}
+__device__ __forceinline__ int strip_count(const StripBatch& b, float thr) {
+  int hits = 0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) hits += (b.s[e].x >= thr) + (b.s[e].y >= thr) + (b.s[e].z >= thr) + (b.s[e].w >= thr);
+  return hits;
+}
+__device__ __forceinline__ int strip_emit(const StripBatch& b, float thr, int2* list, int at) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float v[4] = {b.s[e].x, b.s[e].y, b.s[e].z, b.s[e].w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (v[k] >= thr) {
-        if (at < kCandCap) cand[q * kCandCap + at] = make_int2(n0 + k, __float_as_int(v[k]));
+        if (at < kCandCap) list[at] = make_int2(b.pos[e >> 1] + 4 * (e & 1) + k, __float_as_int(v[k]));
         ++at;
       }
     }
+  }
+  return at;
+}
+__device__ __noinline__ void flush_strip(const float4* ss, const int32_t* sp, int n, bool overflow, float thr,
+                                         int2* cand, int32_t* cand_cnt, int64_t q) {
+  int2* list = cand + q * kCandCap;
+  StripBatch b;
+  strip_load(b, ss, sp, 0, n);
+  int hits = (overflow ? kCandCap + 1 : 0) + strip_count(b, thr);
+  if (n <= 4) {
+    strip_emit(b, thr, list, atomicAdd(cand_cnt + q, hits));
+    return;
+  }
+  for (int g0 = 4; g0 < n; g0 += 4) {
+    StripBatch c;
+    strip_load(c, ss, sp, g0, n);
+    hits += strip_count(c, thr);
+  }
+  int at = strip_emit(b, thr, list, atomicAdd(cand_cnt + q, hits));
+  for (int g0 = 4; g0 < n; g0 += 4) {
+    StripBatch c;
+    strip_load(c, ss, sp, g0, n);
+    at = strip_emit(c, thr, list, at);
   }
 }
 
@@ -372,11 +446,24 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
   const int n_sample = (n_tiles + R - 1) / R;     // phase A: tiles t0, t0 + R, t0 + 2R, ...
   const int n_iter = n_sample + n_tiles;          // phase B: every tile of the chunk
   auto tile_of = [&](int i) { return i < n_sample ? t0 + i * R : t0 + (i - n_sample); };
+  const uint32_t crank = kCluster == 2 ? cluster_ctarank() : 0u;
+  // bring key tile `tile` into ring stage `stg` (one elected thread; the stage's `full` barrier expects a whole image)
+  auto fetch = [&](int tile, int stg) {
+    const uint32_t bar = bar_full + 8 * stg;
+    mbar_arrive_expect_tx(bar, kCopyBytes);
+    if constexpr (kCluster == 2) {
+      constexpr uint32_t half = kCopyBytes / 2;
+      bulk_g2s_multicast(stage0 + stg * kTileBytes + crank * half, p.key_tiles + (int64_t)tile * kTileBytes + crank * half,
+                         half, bar, (uint16_t)3);
+    } else {
+      bulk_g2s(stage0 + stg * kTileBytes, p.key_tiles + (int64_t)tile * kTileBytes, kCopyBytes, bar);
+    }
+  };
 
   if (threadIdx.x == kEpiThreads) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, kCluster);   // one commit per CTA that reads the stage
     }
     for (int a = 0; a < kAccStages; ++a) {
       mbar_init(bar_acc_full + 8 * a, 1);
@@ -384,6 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if constexpr (kCluster == 2) cluster_sync_all();   // the peer's barriers exist before anything is multicast at them
   if (warp == kWarpAlloc) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512)
                  : "memory");
@@ -392,10 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
   // The first ring of key tiles does not depend on anything below: get it in flight now.
   if (threadIdx.x == kEpiThreads) {
     const int pre = n_iter < kStages ? n_iter : kStages;
-    for (int i = 0; i < pre; ++i) {
-      mbar_arrive_expect_tx(bar_full + 8 * i, kCopyBytes);
-      bulk_g2s(stage0 + i * kTileBytes, p.key_tiles + (int64_t)tile_of(i) * kTileBytes, kCopyBytes, bar_full + 8 * i);
-    }
+    for (int i = 0; i < pre; ++i) fetch(tile_of(i), i);
   }
   tc_fence_before();
   __syncthreads();
@@ -445,8 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
         const int s = i % kStages;
         const uint32_t ph = (uint32_t)((i / kStages) & 1);
         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-        mbar_arrive_expect_tx(bar_full + 8 * s, kCopyBytes);
-        bulk_g2s(stage0 + s * kTileBytes, p.key_tiles + (int64_t)tile_of(i) * kTileBytes, kCopyBytes, bar_full + 8 * s);
+        fetch(tile_of(i), s);
       }
     }
   } else if (warp == kWarpIssuer) {
@@ -461,7 +545,9 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
       const int s = i % kStages, a = i % kAccStages;
       // both barriers are polled together: a try_wait costs ~90 clk even when its phase has completed, and the
       // issuer's loop time (waits + issue) is what bounds the tile rate once the epilogue keeps up
-#ifdef EVAVOS_TRACE
+#if (EVAVOS_EXP & 16)
+      mbar_wait(bar_acc_empty + 8 * a, (uint32_t)(((i / kAccStages) & 1) ^ 1));
+#elif defined(EVAVOS_TRACE)
       // trace build: the two waits one after the other, with a timestamp in between (row 0 = key tile landed)
       mbar_wait(bar_full + 8 * s, (uint32_t)((i / kStages) & 1));
       if (lane == 0) EVAVOS_TR(0, i);
@@ -481,7 +567,10 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
         for (int k = 0; k < 4; ++k)  // K = 16 bf16 = 32 B per MMA: advance 2 x 16-byte units inside the swizzle atom
           umma_bf16_ts(d, a_tmem + 8 * k, bdesc0 + 2 * k, kInstrDesc, k > 0 ? 1u : 0u);
         umma_bf16_ts(d, a_tmem + 32, bdesc_aug, kInstrDesc, 1u);  // += -|k|^2/2
-        umma_commit(bar_empty + 8 * s);      // smem stage free once these MMAs have read it
+        // smem stage free once these MMAs have read it (in a cluster: on both CTAs' barriers, each of which
+        // waits for both CTAs before the stage may be overwritten by either CTA's half of the next image)
+        if constexpr (kCluster == 2) umma_commit_multicast(bar_empty + 8 * s, (uint16_t)3);
+        else umma_commit(bar_empty + 8 * s);
         umma_commit(bar_acc_full + 8 * a);   // accumulator tile complete
         EVAVOS_TR(2, i);
       }
@@ -510,6 +599,10 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
       mbar_wait(bar_acc_full + 8 * a, (uint32_t)((i / kAccStages) & 1));
       tc_fence_after();
       if (threadIdx.x == kEpiLeader) EVAVOS_TR(3, i);
+      if constexpr ((EVAVOS_EXP & 32) != 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * a);
+      }
       const int64_t n_first = (int64_t)tile_of(i) * kTilePos + colbase;
 #pragma unroll
       for (int blk = 0; blk < 2; ++blk) {
@@ -521,7 +614,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
 #pragma unroll
           for (int j = 0; j < kCols; ++j) v[j] = kEmptyNh;
         }
-        if (blk == 1) {
+        if (blk == 1 && !(EVAVOS_EXP & 32)) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acc_empty + 8 * a);  // registers hold the tile: release the TMEM stage
@@ -617,6 +710,10 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
         mbar_wait(bar_acc_full + 8 * a, (uint32_t)((i / kAccStages) & 1));
         tc_fence_after();
         if (threadIdx.x == kEpiLeader) EVAVOS_TR(3, i);
+        if constexpr ((EVAVOS_EXP & 32) != 0) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * a);
+        }
         float vv[2 * kCols];
         float* v0 = vv;
         float* v1 = vv + kCols;
@@ -632,9 +729,11 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
 #pragma unroll
           for (int j = 0; j < kCols; ++j) v0[j] = v1[j] = kEmptyNh;
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * a);
+        if constexpr (!(EVAVOS_EXP & 32)) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * a);
+        }
         if (threadIdx.x == kEpiLeader) EVAVOS_TR(4, i);
         if constexpr (!(EVAVOS_EXP & 2)) {
           const int64_t n0 = (int64_t)tile_of(i) * kTilePos + colbase;
@@ -648,8 +747,10 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
           }
           block(v0, (int32_t)n0);
           block(v1, (int32_t)n0 + kCols);
-          if (++since_flush == p.flush_period) {   // every thread of the CTA resolves its strip on the same visit
-            since_flush = 0;
+          // every thread of the CTA resolves its strip on the same visit; a thread whose strip could not take the 8
+          // groups of another visit resolves at once (so `overflow` cannot happen; ~1e-6 per thread and period)
+          if (++since_flush >= p.flush_period || pending > kStrip - 8) {
+            if (since_flush >= p.flush_period) since_flush = 0;
             if (pending > 0 || overflow) flush_strip(ss, sp, pending, overflow, thr, p.cand, p.cand_cnt, q);
             pending = 0;
             overflow = false;
@@ -669,34 +770,44 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
   if (threadIdx.x == 32 * kWarpAlloc) EVAVOS_TR_MARK(59);
+  if constexpr (kCluster == 2) cluster_sync_all();   // no CTA leaves while its peer may still signal its barriers
 }
 
 }  // namespace
 
+// Query tiles the launches cover: rounded up to whole clusters (a padding tile has no live row).
+int64_t score_pass_mtiles(int64_t n_query) {
+  const int64_t mt = ceil_div(n_query, 128);
+  return (mt + kCluster - 1) / kCluster * kCluster;
+}
+
 // Memory-axis chunks per query tile: one wave of CTAs (m_tiles * chunks <= n_sm) whenever possible.
 int score_pass_chunks(int64_t n_pos, int64_t n_query, int n_sm) {
-  const int64_t mt = ceil_div(n_query, 128), nt = ceil_div(n_pos, kTilePos);
+  const int64_t mt = score_pass_mtiles(n_query), nt = ceil_div(n_pos, kTilePos);
   int64_t g = n_sm / mt;
   if (g < 1) g = 1;
   if (g > nt) g = nt;
   return (int)g;
 }
 
-// Phase A contracts every R-th tile.  The expected candidate count grows like ~1.26 k R (plus the error margin),
-// and every candidate costs the epilogue a trip off its fast path; the sample must also keep >= ~48 tiles so that
-// 128 classes over it say something.  Measured on B200: R = 2 for long banks.
-int score_pass_sample_stride(int64_t n_pos, int requested) {
+// Phase A contracts every R-th tile of a chunk.  The expected candidate count grows like ~1.26 k R (plus the error
+// margin) and every candidate costs the candidate pass a trip off its fast path, while the threshold pass shrinks
+// by 1/R.  Measured on B200 (filter time in us, R = 1 | 2 | 3 | 4):
+//   cfg2 (23 tiles per CTA)    43 | 46 | 55 | 59        cfg4 (230)  146 | 130 | 147 | 154       cfg5 (1 594)  804 | 688 | 758 | 790
+// so R = 2 once a CTA's chunk is long enough for the saved half sweep to outweigh the denser hits, else R = 1.
+int score_pass_sample_stride(int64_t n_pos, int n_chunks, int requested) {
   const int64_t nt = ceil_div(n_pos, kTilePos);
-  int r = requested > 0 ? requested : 2;
+  const int64_t per_cta = nt / (n_chunks > 0 ? n_chunks : 1);
+  int r = requested > 0 ? requested : (per_cta >= 64 ? 2 : 1);
   if (r > 8) r = 8;
-  const int64_t cap = nt / 48;
+  const int64_t cap = nt / 48;       // the sample keeps >= ~48 tiles so that 128 classes over it say something
   if (r > cap) r = (int)cap;
   if (r < 1) r = 1;
   return r;
 }
 
 size_t score_pass_strip_bytes(int64_t n_query, int n_chunks, int n_sm) {
-  const int64_t mt = ceil_div(n_query, 128);
+  const int64_t mt = score_pass_mtiles(n_query);
   const int64_t per_launch = n_chunks > 1 ? mt : (mt < n_sm ? mt : n_sm);
   return (size_t)per_launch * n_chunks * kStrip * kEpiThreads * (2 * sizeof(float4) + sizeof(int32_t));
 }
@@ -722,8 +833,9 @@ int launch_score_select(const float* query, int64_t query_ch_stride, const void*
     EVAVOS_CUDA_OK(cudaFuncSetAttribute(score_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  const int mt_total = (int)ceil_div(n_query, 128);
-  const int mt_per_launch = n_chunks > 1 ? mt_total : (mt_total < n_sm ? mt_total : n_sm);
+  const int mt_total = (int)score_pass_mtiles(n_query);
+  const int wave = n_sm / kCluster * kCluster;
+  const int mt_per_launch = n_chunks > 1 ? mt_total : (mt_total < wave ? mt_total : wave);
   for (int m0 = 0; m0 < mt_total; m0 += mt_per_launch) {
     PassParams p;
     p.query = query;
@@ -750,16 +862,29 @@ int launch_score_select(const float* query, int64_t query_ch_stride, const void*
     {
       // expected staged groups per thread and visit: ~1.8 k R candidates per query, a visit covers 64 positions
       const double per_visit = 1.8 * top_k * sample_stride * 64.0 / (double)n_pos;
-      double period = 3.0 / per_visit;            // ~3 groups per strip (of kStrip = 16) when it is resolved
+      double period = 4.0 / per_visit;            // ~4 groups per strip (of kStrip = 24) when it is resolved
       if (period < 4.0) period = 4.0;
       if (period > 1.0e6) period = 1.0e6;
       p.flush_period = (int)period;
     }
     const unsigned grid = (unsigned)(p.n_mtiles * n_chunks);
     EVAVOS_CUDA_OK(cudaMemsetAsync(grid_counter, 0, sizeof(unsigned int) * (size_t)p.n_mtiles, st));
-    void* args[] = {&p};
-    EVAVOS_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(score_select_kernel), dim3(grid),
-                                               dim3(kThreads), args, kSmemBytes, st));
+    // cooperative (the grid barrier needs every CTA resident) and, with EVAVOS_CLUSTER = 2, in clusters of two
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = kCluster;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = kCluster > 1 ? 2 : 1;
+    EVAVOS_CUDA_OK(cudaLaunchKernelEx(&cfg, score_select_kernel, p));
   }
   return EVAVOS_OK;
 }

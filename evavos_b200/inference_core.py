@@ -39,7 +39,10 @@ class InferenceCore:
     mem_freq - period at which propagated frames are added to the memory bank
     """
 
-    def __init__(self, prop_net, fuse_net, images, num_objects, mem_profile=0, mem_freq=5, device="cuda"):
+    def __init__(self, prop_net, fuse_net, images, num_objects, mem_profile=0, mem_freq=5, device="cuda", *,
+                 amp=False):
+        """``amp`` (keyword of this engine, not of the reference): run the conv encoders / decoder under bf16 autocast
+        in channels_last; keys, values and the memory read stay fp32."""
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("evavos_b200.InferenceCore needs a CUDA device: the memory read has no CPU path")
@@ -49,6 +52,9 @@ class InferenceCore:
         self.mem_profile = mem_profile
         self.mem_freq = mem_freq
         self.device = dev
+        self.amp = bool(amp)
+        if self.amp:
+            self.prop_net = self.prop_net.to(memory_format=torch.channels_last)
 
         if mem_profile == 0:
             self.data_dev, self.result_dev, self.k_buf_size, self.i_buf_size = dev, dev, 105, -1
@@ -117,8 +123,22 @@ class InferenceCore:
         if idx not in self.key_buf:
             if len(self.key_buf) > self.k_buf_size:
                 self.key_buf = {}
-            self.key_buf[idx] = self.prop_net.encode_key(self.get_image_buffered(idx))
+            self.key_buf[idx] = self._encode_key(self.get_image_buffered(idx))
         return self.key_buf[idx]
+
+    def _autocast(self):
+        return torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp)
+
+    def _encode_key(self, frames):
+        with self._autocast():
+            outs = self.prop_net.encode_key(frames.contiguous(memory_format=torch.channels_last) if self.amp else frames)
+        # the memory key (and everything the read touches) stays fp32; the skip features keep the conv dtype
+        return (outs[0].float(),) + tuple(outs[1:]) if self.amp else outs
+
+    def _encode_value(self, frame, qf16, masks):
+        with self._autocast():
+            v = self.prop_net.encode_value(frame, qf16, masks)
+        return v.float() if self.amp else v
 
     def _key_feats(self, frames):
         """Key features of several frames: the ones not cached yet go through the encoder as ONE batch (they only
@@ -126,7 +146,7 @@ class InferenceCore:
         missing = [ti for ti in frames if ti not in self.key_buf]
         if len(missing) > 1 and self._batch_frames:
             batch = torch.cat([self.get_image_buffered(ti) for ti in missing], 0)
-            outs = self.prop_net.encode_key(batch)
+            outs = self._encode_key(batch)
             fresh = {}
             for j, ti in enumerate(missing):
                 if len(self.key_buf) > self.k_buf_size:
@@ -140,8 +160,9 @@ class InferenceCore:
     # ------------------------------------------------------------------ pieces of segment_with_query
     def _decode(self, readout, qf8, qf4, qv16):
         k = readout.shape[0]
-        m4 = torch.cat([readout, qv16.expand(k, -1, -1, -1)], 1)
-        return torch.sigmoid(self.prop_net.decoder(m4, qf8, qf4))
+        m4 = torch.cat([readout, qv16.expand(k, -1, -1, -1).to(readout.dtype)], 1)
+        with self._autocast():
+            return torch.sigmoid(self.prop_net.decoder(m4, qf8, qf4)).float()
 
     def _grow_certain(self, key_k, key_v):
         """certain_mem = cat(certain_mem, new frame) (inference_core.py:235-240) without re-allocating every time."""
@@ -199,22 +220,28 @@ class InferenceCore:
             pos += len(seg)
             feats = self._key_feats(seg)
             qk = torch.stack([f[0] for f in feats], 2) if len(seg) > 1 else feats[0][0]
-            readout, _ = self._read(bank, qk)
-            if len(seg) == 1:
-                readout = readout.unsqueeze(2)
-            decoded = None
-            if len(seg) > 1 and self._batch_frames:
-                # the frames of a segment are independent given the bank: one decoder pass for all of them
-                decoded = self.prop_net.decode_frames(readout, torch.cat([f[3] for f in feats], 0),
-                                                      torch.cat([f[4] for f in feats], 0),
-                                                      torch.cat([f[1] for f in feats], 0))
+            decoded = readout = None
+            if self._batch_frames:
+                # The frames of a segment are independent given the bank: one read and one decoder pass for all of
+                # them.  The read kernel writes straight into the readout half of the decoder input (F,K,2*CV,H,W);
+                # the other half is the frames' query value feature - no torch.cat (prop_net.py:189-190).
+                m4 = torch.empty((len(seg), K, 2 * CV, H, W), dtype=torch.float32, device=self.device)
+                self._read(bank, qk, out=m4 if len(seg) > 1 else m4[0])
+                m4[:, :, CV:] = torch.cat([f[1] for f in feats], 0).unsqueeze(1)
+                with self._autocast():
+                    decoded = self.prop_net.decode_input(m4, torch.cat([f[3] for f in feats], 0),
+                                                         torch.cat([f[4] for f in feats], 0)).float()
+            else:
+                readout, _ = self._read(bank, qk)
+                if len(seg) == 1:
+                    readout = readout.unsqueeze(2)
             for j, ti in enumerate(seg):
                 k16, qv16, qf16, qf8, qf4 = feats[j]
                 out_mask = decoded[j] if decoded is not None else self._decode(readout[:, :, j], qf8, qf4, qv16)
                 out_mask = aggregate_wbg(out_mask, keep_bg=True)
 
                 if ti != end and abs(ti - last_ti) >= self.mem_freq:
-                    new_v = self.prop_net.encode_value(self.get_image_buffered(ti), qf16, out_mask[1:])
+                    new_v = self._encode_value(self.get_image_buffered(ti), qf16, out_mask[1:])
                     bank.append(k16, new_v)
                     last_ti = ti
 
@@ -225,9 +252,9 @@ class InferenceCore:
                     self.prob[:, ti] = out_mask.to(self.result_dev)
         return closest_ti
 
-    def _read(self, bank, qk):
+    def _read(self, bank, qk, out=None):
         from .memory_reader import memory_read
-        return memory_read(bank, qk, self._reader.top_k)
+        return memory_read(bank, qk, self._reader.top_k, out=out)
 
     def fuse_one_frame(self, tc, tr, ti, prev_mask, curr_mask, mk16, qk16):
         assert (tc < ti < tr or tr < ti < tc)
@@ -256,7 +283,7 @@ class InferenceCore:
         self.prob[:, idx] = mask
         key_k, _, qf16, _, _ = self.get_key_feat_buffered(idx)
         key_k = key_k.unsqueeze(2)
-        key_v = self.prop_net.encode_value(self.get_image_buffered(idx), qf16, mask[1:] if scribble else mask)
+        key_v = self._encode_value(self.get_image_buffered(idx), qf16, mask[1:] if scribble else mask)
 
         self._grow_certain(key_k, key_v)
 

@@ -81,8 +81,9 @@ def memory_read(bank: MemoryBank, qk: torch.Tensor, top_k: int = 50, n_frames: i
 
     ``sample_stride`` (tensor path): the filter's threshold pass contracts every sample_stride-th key tile
     (None/0: the library's choice, or $EVAVOS_SAMPLE_STRIDE when set - a tuning knob, results do not depend on it).
-    ``out``: optional pre-allocated fp32 destination viewed as (K, >=CV, nq) - e.g. the first CV channels of the
-    decoder's (K, 2*CV, H, W) input, so that no torch.cat is needed (prop_net.py:189-190).
+    ``out``: optional pre-allocated fp32 destination - (K, >=CV, *spatial), e.g. the first CV channels of the
+    decoder's (K, 2*CV, H, W) input, or, for a (1,CK,F,H,W) query batch, frame-major (F, K, >=CV, H, W) - so that no
+    torch.cat is needed (prop_net.py:189-190).
     ``peers`` (an ``_lib.Peers``) / ``peer_gather_offset``: sharded read - the finalizer also stores every query's
     list into all ranks' exchange buffers (see include/evavos.h, EvavosMemReadArgs.peers).
     Returns (readout (K,CV,[F,]H,W) or None, TopKAffinity or None).
@@ -111,9 +112,17 @@ def memory_read(bank: MemoryBank, qk: torch.Tensor, top_k: int = 50, n_frames: i
         a.peer_gather_offset = int(peer_gather_offset)
     idx = weight = score = None
     user_out = out
+    frame_major = False
     if want_readout:
         if out is None:
             out = torch.empty((bank.K, bank.CV, nq), dtype=torch.float32, device=dev)
+        elif len(spatial) == 3 and out.dim() == 5 and tuple(out.shape) == (spatial[0], bank.K, out.shape[2]) + spatial[1:]:
+            # frame-major (F, K, C>=CV, H, W): one destination block per query frame
+            if out.dtype != torch.float32 or out.device != dev or out.shape[2] < bank.CV or not out[0, 0, 0].is_contiguous():
+                raise ValueError(f"out {tuple(out.shape)} cannot receive a frame-major readout")
+            a.readout_obj_stride, a.readout_ch_stride = out.stride(1), out.stride(2)
+            a.queries_per_frame, a.readout_frame_stride = spatial[1] * spatial[2], out.stride(0)
+            frame_major = True
         else:
             # (K, C>=CV, *spatial) fp32 with contiguous positions: the kernel takes object / channel strides
             if out.dtype != torch.float32 or out.device != dev or out.shape[0] != bank.K or out.shape[1] < bank.CV \
@@ -139,7 +148,10 @@ def memory_read(bank: MemoryBank, qk: torch.Tensor, top_k: int = 50, n_frames: i
         _lib.check(lib.evavos_memread(ctypes.byref(a), _lib.current_stream_ptr(dev)))
     aff = TopKAffinity(idx, weight, score, n_pos, bank.H, bank.W) if want_topk else None
     if want_readout:
-        out = out.view(bank.K, bank.CV, *spatial) if user_out is None else user_out[:, :bank.CV]
+        if user_out is None:
+            out = out.view(bank.K, bank.CV, *spatial)
+        else:
+            out = user_out[:, :, :bank.CV] if frame_major else user_out[:, :bank.CV]
     else:
         out = None
     return out, aff

@@ -254,9 +254,16 @@ class PropagationNetwork(nn.Module):
         ``Decoder.forward`` (prop_net.py:13-30); the per-frame skip features, which the single-frame path broadcasts
         over the K objects inside ``skip_conv(skip) + up``, are repeated explicitly so that one pass covers F*K maps.
         """
-        k, _, f, hh, ww = readout.shape
-        dec = self.decoder
+        k = readout.shape[0]
         m4 = torch.cat([readout.permute(2, 0, 1, 3, 4), qv16.unsqueeze(1).expand(-1, k, -1, -1, -1)], 2)
+        return self.decode_input(m4, qf8, qf4)
+
+    def decode_input(self, m4, qf8, qf4):
+        """The decoder on an assembled input: m4 (F,K,1024,H,W) = [memory readout | query value feature] per frame and
+        object (prop_net.py:189-190).  InferenceCore lets the read kernel write the readout half of m4 in place, so
+        the (K,1024,H,W) ``torch.cat`` of the reference never happens."""
+        f, k, _, hh, ww = m4.shape
+        dec = self.decoder
         x = dec.compress(m4.reshape(f * k, -1, hh, ww))
         for block, skip in ((dec.up_16_8, qf8), (dec.up_8_4, qf4)):
             up = F.interpolate(x, scale_factor=block.scale_factor, mode="bilinear", align_corners=False)

@@ -143,6 +143,12 @@ typedef struct EvavosMemReadArgs {
      read, done by the epilogue of the kernel that produces the lists (evavos_topk_merge_gathered consumes it). */
   const EvavosPeers* peers;
   int64_t peer_gather_offset;
+  /* Several query frames in one launch (n_query = frames * queries_per_frame), each frame with its own destination
+     block: query q = f * queries_per_frame + p of (object o, channel c) is written to
+     readout[f * readout_frame_stride + o * readout_obj_stride + c * readout_ch_stride + p] - e.g. straight into the
+     decoder's (F, K, 2*CV, H, W) input (prop_net.py:189-190 without the cat).  0 -> one block, offset q. */
+  int64_t queries_per_frame;
+  int64_t readout_frame_stride;
 } EvavosMemReadArgs;
 
 int evavos_abi_version(void);

@@ -91,3 +91,28 @@ def test_cpu_device_rejected():
     prop, fuse = _nets()
     with pytest.raises(RuntimeError, match="CUDA"):
         ev.InferenceCore(prop, fuse, torch.zeros(1, 2, 3, 128, 160), 1, device="cpu")
+
+
+def test_bf16_channels_last_convs_agree_with_fp32():
+    """``amp=True`` runs the conv encoders / decoder under bf16 autocast in channels_last; the keys,
+    the values handed to the bank and the memory read stay fp32.  With seeded RANDOM weights (no checkpoint exists
+    offline) the probabilities move by ~1e-2 and only pixels the fp32 run itself leaves near 0.5 may flip."""
+    import evavos_b200 as ev
+    prop, fuse = _nets()
+    g = load("e2e_k1.npz")
+    images = torch.from_numpy(g["images"])
+    mask = torch.from_numpy(g["mask_0"])
+    a = ev.InferenceCore(prop, fuse, images, 1, mem_freq=2, device="cuda:0")
+    ma = a.interact(mask, 0)
+    b = ev.InferenceCore(copy.deepcopy(prop), fuse, images, 1, mem_freq=2, device="cuda:0", amp=True)
+    mb = b.interact(mask, 0)
+    assert b.prob.dtype == torch.float32
+    d = (a.prob - b.prob).abs()
+    agree = float((ma == mb).mean())
+    print(f"amp vs fp32: max |dp| {d.max().item():.4f}, mean |dp| {d.mean().item():.5f}, mask agreement {agree:.5f}")
+    assert d.mean().item() < 2e-2
+    decided = ((a.prob[1] - 0.5).abs() > 0.1).cpu().numpy()[:, 0]          # fp32 run at least 0.1 away from the boundary
+    lw, uw, lh, uh = (int(x) for x in g["pad"])
+    decided = decided[:, lh:decided.shape[1] - uh or None, lw:decided.shape[2] - uw or None]
+    assert ((ma != mb) & decided).mean() < 1e-3
+    assert agree > 0.97

@@ -26,7 +26,9 @@ def test_signatures_match_reference_api():
     """constructor / method names and defaults the callers rely on."""
     from evavos_b200 import EvalMemoryReader, InferenceCore, PropagationNetwork, aggregate_wbg
     sig = inspect.signature(InferenceCore.__init__)
-    assert list(sig.parameters)[1:] == ["prop_net", "fuse_net", "images", "num_objects", "mem_profile", "mem_freq", "device"]
+    assert list(sig.parameters)[1:8] == ["prop_net", "fuse_net", "images", "num_objects", "mem_profile", "mem_freq", "device"]
+    assert all(sig.parameters[n].kind is inspect.Parameter.KEYWORD_ONLY and sig.parameters[n].default is not inspect.Parameter.empty
+               for n in list(sig.parameters)[8:])     # engine-only options are optional keywords
     assert sig.parameters["mem_profile"].default == 0 and sig.parameters["mem_freq"].default == 5
     assert sig.parameters["device"].default == "cuda"
     assert list(inspect.signature(InferenceCore.interact).parameters)[1:] == ["mask", "idx", "scribble"]
