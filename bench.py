@@ -454,6 +454,9 @@ def run_sharded(args, cfg, rank, world, local_rank, dist=None, emit=True):
             line.update({"warmup": args.warmup, "higher_is_better": True, "vs_baseline": None,
                          "gpu_launches": (3 + 2) * steps})
             print(json.dumps(line), flush=True)
+    for b in banks:
+        if hasattr(b, "close"):
+            b.close()
     del banks, full, queries
     torch.cuda.empty_cache()
     if own_pg:

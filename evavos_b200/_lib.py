@@ -69,6 +69,11 @@ SIGNATURES = {
     "evavos_memread": (_c_i32, [ctypes.POINTER(MemReadArgs), _c_vp]),
     "evavos_readout": (_c_i32, [ctypes.POINTER(BankShadow), _c_vp, _c_vp, _c_i64, _c_i32, _c_vp, _c_i64, _c_i64, _c_vp]),
     "evavos_readout_qmajor": (_c_i32, [ctypes.POINTER(BankShadow), _c_vp, _c_vp, _c_i64, _c_i32, _c_vp, _c_vp]),
+    "evavos_peer_enable": (_c_i32, [_c_i32]),
+    "evavos_peer_buffer_alloc": (_c_i32, [_c_i64, ctypes.POINTER(_c_vp), ctypes.c_char_p]),
+    "evavos_peer_buffer_open": (_c_i32, [ctypes.c_char_p, ctypes.POINTER(_c_vp)]),
+    "evavos_peer_buffer_close": (_c_i32, [_c_vp]),
+    "evavos_peer_buffer_free": (_c_i32, [_c_vp]),
     "evavos_peer_barrier": (_c_i32, [ctypes.POINTER(Peers), _c_i64, ctypes.c_uint32, _c_vp]),
     "evavos_peer_reduce_scatter": (_c_i32, [ctypes.POINTER(Peers), _c_i64, _c_i32, _c_i64, _c_i64, _c_vp, _c_i64, _c_vp]),
     "evavos_jf_workspace_bytes": (ctypes.c_size_t, [_c_i64, _c_i32, _c_i32]),

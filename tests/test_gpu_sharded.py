@@ -99,6 +99,7 @@ def _sharded_worker(rank, world, port, ret, backend, same_device):
             if backend == "nccl":      # replicated form (all-gather of the slices)
                 out = bank.read(qk.to(dev), 50)
                 assert onp.rel_l2(out.cpu().numpy().reshape(ro.shape), ro) < 1e-5
+            bank.close()
         ret[rank] = True
     finally:
         dist.destroy_process_group()
