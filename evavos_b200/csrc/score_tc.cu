@@ -71,7 +71,11 @@ namespace {
 constexpr int kCluster = EVAVOS_CLUSTER;
 static_assert(kCluster == 1 || kCluster == 2, "clusters of 1 or 2 CTAs");
 constexpr int kStages = EVAVOS_STAGES;
-constexpr int kAccStages = 3;   // 3 x 128 accumulator columns; the query operand lives in columns [384, 424)
+#ifndef EVAVOS_ACC_STAGES
+#define EVAVOS_ACC_STAGES 3
+#endif
+constexpr int kAccStages = EVAVOS_ACC_STAGES;   // 3 x 128 accumulator columns; the query operand lives in columns [384, 424)
+                                                // (4 only with -DEVAVOS_SS: the query operand then sits in shared memory)
 constexpr int kQueryCol = 384;
 constexpr int kEpiWarps = 16;   // two groups of 8 warps on alternate iterations
 constexpr int kEpiThreads = 32 * kEpiWarps;
@@ -89,7 +93,13 @@ constexpr int kCols = 32;       // accumulator columns per tcgen05.ld
 constexpr int kClasses = 128;   // column classes per query and chunk (phase A)
 constexpr int kStrip = 24;      // staged 8-score groups per epilogue thread before they are resolved into the list
 constexpr int kBarBytes = 256;
-constexpr int kSmemBytes = kTileBytes * kStages + kBarBytes + 1024;
+// -DEVAVOS_SS: the query operand as a shared-memory tile image (SS-form MMAs) instead of TMEM (TS form) - experiment.
+#ifdef EVAVOS_SS
+constexpr int kQueryImageBytes = kTileBytes;
+#else
+constexpr int kQueryImageBytes = 0;
+#endif
+constexpr int kSmemBytes = kTileBytes * kStages + kQueryImageBytes + kBarBytes + 1024;
 constexpr uint32_t kCopyBytes = (EVAVOS_EXP & 4) ? 4096 : kTileBytes;   // bytes the producers move per tile image
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -172,6 +182,15 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
@@ -423,14 +442,15 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw);
   const uint32_t stage0 = base;
-  const uint32_t bars = base + kTileBytes * kStages;
+  const uint32_t qimg = base + kTileBytes * kStages;   // (EVAVOS_SS) query operand image
+  const uint32_t bars = qimg + kQueryImageBytes;
   const uint32_t bar_full = bars;                                // [kStages]
   const uint32_t bar_empty = bars + 8 * kStages;                 // [kStages]
   const uint32_t bar_acc_full = bars + 16 * kStages;             // [kAccStages]
   const uint32_t bar_acc_empty = bar_acc_full + 8 * kAccStages;  // [kAccStages]
   const uint32_t tmem_slot = bar_acc_empty + 8 * kAccStages;
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + kTileBytes * kStages + 16 * kStages + 16 * kAccStages);
+      reinterpret_cast<volatile uint32_t*>(base_ptr + kTileBytes * kStages + kQueryImageBytes + 16 * kStages + 16 * kAccStages);
 
   if (threadIdx.x == kEpiThreads) EVAVOS_TR_MARK(56);
   // warp index through a shuffle: the compiler then knows it is warp-uniform, keeps everything derived from it
@@ -497,6 +517,23 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
     float f[64];
 #pragma unroll
     for (int c = 0; c < 64; ++c) f[c] = live ? __ldg(p.query + (int64_t)c * p.query_ch_stride + qrow) : 0.f;
+#ifdef EVAVOS_SS
+    uint8_t* img = base_ptr + kTileBytes * kStages;
+#pragma unroll
+    for (int chunk = 0; chunk < 8; ++chunk) {   // 8 bf16 = 16 bytes per chunk, SWIZZLE_128B K-major like a key tile
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 v2 = __floats2bfloat162_rn(f[chunk * 8 + 2 * j], f[chunk * 8 + 2 * j + 1]);
+        w[j] = *reinterpret_cast<const uint32_t*>(&v2);
+      }
+      *reinterpret_cast<uint4*>(img + swizzle128_offset(r, chunk)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    *reinterpret_cast<uint4*>(img + kTileKeyBytes + swizzle32_offset(r, 0)) =
+        make_uint4(live ? 0x3f803f80u : 0u, live ? 0x00003f80u : 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(img + kTileKeyBytes + swizzle32_offset(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
+#else
     const uint32_t a_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + kQueryCol;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -511,6 +548,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
     const uint32_t aug[8] = {live ? 0x3f803f80u : 0u, live ? 0x00003f80u : 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     tmem_st8(a_addr + 32, aug);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -563,10 +601,19 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
         const uint64_t bdesc0 = make_desc(st, 1024, kLayoutSw128);
         const uint64_t bdesc_aug = make_desc(st + kTileKeyBytes, 256, kLayoutSw32);
         const uint32_t d = tmem_base + a * 128;
+#ifdef EVAVOS_SS
+        const uint64_t adesc0 = make_desc(qimg, 1024, kLayoutSw128);
+        const uint64_t adesc_aug = make_desc(qimg + kTileKeyBytes, 256, kLayoutSw32);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(d, adesc0 + 2 * k, bdesc0 + 2 * k, kInstrDesc, k > 0 ? 1u : 0u);
+        umma_bf16_ss(d, adesc_aug, bdesc_aug, kInstrDesc, 1u);
+        (void)a_tmem;
+#else
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // K = 16 bf16 = 32 B per MMA: advance 2 x 16-byte units inside the swizzle atom
           umma_bf16_ts(d, a_tmem + 8 * k, bdesc0 + 2 * k, kInstrDesc, k > 0 ? 1u : 0u);
         umma_bf16_ts(d, a_tmem + 32, bdesc_aug, kInstrDesc, 1u);  // += -|k|^2/2
+#endif
         // smem stage free once these MMAs have read it (in a cluster: on both CTAs' barriers, each of which
         // waits for both CTAs before the stage may be overwritten by either CTA's half of the next image)
         if constexpr (kCluster == 2) umma_commit_multicast(bar_empty + 8 * s, (uint16_t)3);
@@ -720,6 +767,10 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
         if constexpr (!(EVAVOS_EXP & 1)) {
 #ifdef EVAVOS_LD64
           tmem_ld64(lane_addr + (uint32_t)(a * 128 + colbase), vv);   // one 64-column load instead of two of 32
+#elif defined(EVAVOS_SEQLD)
+          tmem_ld32(lane_addr + (uint32_t)(a * 128 + colbase), v0);   // experiment: one load in flight per warp
+          tmem_ld_wait();
+          tmem_ld32(lane_addr + (uint32_t)(a * 128 + colbase + kCols), v1);
 #else
           tmem_ld32(lane_addr + (uint32_t)(a * 128 + colbase), v0);
           tmem_ld32(lane_addr + (uint32_t)(a * 128 + colbase + kCols), v1);
