@@ -108,9 +108,11 @@ __device__ __forceinline__ uint32_t kth_largest_bound(const uint32_t* key, int k
 // Cut the scored candidate list down to the entries that can still be in the exact top-k and leave their positions
 // in sm.keys[0..ns).  theta = (a lower bound of) the k-th largest filter score in the list: k listed positions reach
 // it, so the k-th best exact score is >= theta - eps and every member of the exact top-k has a filter score
-// >= theta - 2 eps.  Returns ns, or -1 when more than kMaxSurvivors entries survive (massive near-ties).
+// >= theta - 2 eps.  Returns ns.  The survivors' positions are also compacted IN PLACE into list[0..ns).x (a slot
+// never lies beyond the entries already read), which is where a query with more than kMaxSurvivors of them - a big
+// cluster of near-ties, e.g. a static background seen in hundreds of memory frames - is finished from, in batches.
 template <int NJ>
-__device__ __forceinline__ int prefilter_candidates(FinalizeWarpSmem& sm, const int2* list, int n, int k, float two_eps,
+__device__ __forceinline__ int prefilter_candidates(FinalizeWarpSmem& sm, int2* list, int n, int k, float two_eps,
                                                     int lane) {
   uint32_t key[NJ];
 #pragma unroll
@@ -128,11 +130,69 @@ __device__ __forceinline__ int prefilter_candidates(FinalizeWarpSmem& sm, const 
     const unsigned m = __ballot_sync(0xffffffffu, pass);
     if (pass) {
       const int slot = ns + __popc(m & ((1u << lane) - 1u));
-      if (slot < kMaxSurvivors) sm.keys[slot] = (unsigned long long)(uint32_t)__ldcg(&list[e].x);
+      const int32_t pos = __ldcg(&list[e].x);
+      if (slot < kMaxSurvivors) sm.keys[slot] = (unsigned long long)(uint32_t)pos;
+      list[slot].x = pos;
     }
     ns += __popc(m);
   }
-  return ns <= kMaxSurvivors ? ns : -1;
+  return ns;
+}
+
+// sm.keys[0..n) hold positions: replace them by the exact (score, position) keys.  32 rows per round.
+__device__ __forceinline__ void rescore_rows(FinalizeWarpSmem& sm, int n, const float* __restrict__ key_pm, int CK,
+                                             float qq, float inv_sqrt_ck, int lane) {
+  for (int base = 0; base < n; base += 32) {
+    const int nrows = min(32, n - base);
+    float s = 0.f;
+    int32_t pos = 0;
+    if (CK == 64) {
+      // Rows go through shared memory: half a warp fetches one 256-byte row (two full lines per row and
+      // instruction instead of 32 partial ones when every lane walks its own row), then lane t rescoring row t
+      // reads it back with the FMA order of dot_row.
+      // (all 16 loads of a lane in flight before the first store: the rows come from HBM, one latency per round)
+      float4 buf[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int r = (lane >> 4) + 2 * u;
+        if (r < nrows) {
+          const int32_t nr = (int32_t)(uint32_t)sm.keys[base + r];
+          buf[u] = __ldg(reinterpret_cast<const float4*>(key_pm + (int64_t)nr * 64) + (lane & 15));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int r = (lane >> 4) + 2 * u;
+        if (r < nrows) *reinterpret_cast<float4*>(&sm.rows[r][4 * (lane & 15)]) = buf[u];
+      }
+      __syncwarp();
+      if (lane < nrows) {
+        pos = (int32_t)(uint32_t)sm.keys[base + lane];
+        float kk, kq;
+        dot_row_smem64(reinterpret_cast<const float4*>(sm.rows[lane]), sm.qs, kk, kq);
+        s = affinity_from_parts(kk, kq, qq, inv_sqrt_ck);
+      }
+    } else if (lane < nrows) {
+      pos = (int32_t)(uint32_t)sm.keys[base + lane];
+      float kk, kq;
+      dot_row(reinterpret_cast<const float4*>(key_pm + (int64_t)pos * CK), sm.qs, CK, kk, kq);
+      s = affinity_from_parts(kk, kq, qq, inv_sqrt_ck);
+    }
+    __syncwarp();
+    if (lane < nrows) sm.keys[base + lane] = score_key(s, pos);
+  }
+  __syncwarp();
+}
+
+// All-pairs rank of the unique keys sm.keys[0..n): the `take` largest go to sm.sel, best first.
+__device__ __forceinline__ void rank_into_sel(FinalizeWarpSmem& sm, int n, int take, int lane) {
+  for (int c = lane; c < n; c += 32) {
+    const unsigned long long mine = sm.keys[c];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += sm.keys[j] > mine ? 1 : 0;  // broadcast reads
+    if (rank < take) sm.sel[rank] = mine;
+  }
+  __syncwarp();
 }
 
 // Exact top-k of one query over ALL positions by one warp: a sorted list in sm.sel, 32 exact scores per step, an
@@ -199,8 +259,9 @@ __device__ __forceinline__ void finalize_query_warp(FinalizeWarpSmem& sm, int la
   const float qq = (CK == 64) ? sumsq64_warp(sm.qs, lane) : sumsq(sm.qs, CK);
   const int2* list = cand + q * kCandCap;
 
-  int ns = -1;   // survivors in sm.keys, or -1: take the exact path
+  int ns = -1;   // survivors (positions in sm.keys when <= kMaxSurvivors, else in list[].x), or -1: the exact path
   if (cnt_raw <= kCandCap) {
+    int2* wlist = const_cast<int2*>(list);   // the lists are workspace: the cut compacts them in place
     if (!scored) {
       ns = min(cnt_raw, kMaxSurvivors);
       for (int e = lane; e < ns; e += 32) sm.keys[e] = (unsigned long long)(uint32_t)__ldcg(&list[e].x);
@@ -210,64 +271,34 @@ __device__ __forceinline__ void finalize_query_warp(FinalizeWarpSmem& sm, int la
       if (cnt_raw <= top_k + 32) {   // a list this short is not worth cutting: rescore all of it
         ns = cnt_raw;
         for (int e = lane; e < ns; e += 32) sm.keys[e] = (unsigned long long)(uint32_t)__ldcg(&list[e].x);
-      } else if (cnt_raw <= 256) ns = prefilter_candidates<8>(sm, list, cnt_raw, k, two_eps, lane);
-      else if (cnt_raw <= 512) ns = prefilter_candidates<16>(sm, list, cnt_raw, k, two_eps, lane);
-      else ns = prefilter_candidates<32>(sm, list, cnt_raw, k, two_eps, lane);
+      } else if (cnt_raw <= 256) ns = prefilter_candidates<8>(sm, wlist, cnt_raw, k, two_eps, lane);
+      else if (cnt_raw <= 512) ns = prefilter_candidates<16>(sm, wlist, cnt_raw, k, two_eps, lane);
+      else ns = prefilter_candidates<32>(sm, wlist, cnt_raw, k, two_eps, lane);
     }
   }
   int take;
+  __syncwarp();
   if (ns < 0) {
-    __syncwarp();
     take = exact_topk_warp(sm, key_pm, CK, n_pos, top_k, qq, inv_sqrt_ck, lane);
-  } else {
-    __syncwarp();
-    // exact rescoring, 32 survivors per round
-    for (int base = 0; base < ns; base += 32) {
-      const int nrows = min(32, ns - base);
-      float s = 0.f;
-      int32_t n = 0;
-      if (CK == 64) {
-        // Rows go through shared memory: half a warp fetches one 256-byte row (two full lines per row and
-        // instruction instead of 32 partial ones when every lane walks its own row), then lane t rescoring row t
-        // reads it back with the FMA order of dot_row.
-        // (all 16 loads of a lane in flight before the first store: the rows come from HBM, one latency per round)
-        float4 buf[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int r = (lane >> 4) + 2 * u;
-          if (r < nrows) {
-            const int32_t nr = (int32_t)(uint32_t)sm.keys[base + r];
-            buf[u] = __ldg(reinterpret_cast<const float4*>(key_pm + (int64_t)nr * 64) + (lane & 15));
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int r = (lane >> 4) + 2 * u;
-          if (r < nrows) *reinterpret_cast<float4*>(&sm.rows[r][4 * (lane & 15)]) = buf[u];
-        }
-        __syncwarp();
-        if (lane < nrows) {
-          n = (int32_t)(uint32_t)sm.keys[base + lane];
-          float kk, kq;
-          dot_row_smem64(reinterpret_cast<const float4*>(sm.rows[lane]), sm.qs, kk, kq);
-          s = affinity_from_parts(kk, kq, qq, inv_sqrt_ck);
-        }
-      } else if (lane < nrows) {
-        n = (int32_t)(uint32_t)sm.keys[base + lane];
-        float kk, kq;
-        dot_row(reinterpret_cast<const float4*>(key_pm + (int64_t)n * CK), sm.qs, CK, kk, kq);
-        s = affinity_from_parts(kk, kq, qq, inv_sqrt_ck);
-      }
-      __syncwarp();
-      if (lane < nrows) sm.keys[base + lane] = score_key(s, n);
-    }
-    __syncwarp();
+  } else if (ns <= kMaxSurvivors) {
+    rescore_rows(sm, ns, key_pm, CK, qq, inv_sqrt_ck, lane);
     take = min(top_k, ns);
-    for (int c = lane; c < ns; c += 32) {
-      const unsigned long long mine = sm.keys[c];
-      int rank = 0;
-      for (int j = 0; j < ns; ++j) rank += sm.keys[j] > mine ? 1 : 0;  // broadcast reads; keys are unique
-      if (rank < take) sm.sel[rank] = mine;
+    rank_into_sel(sm, ns, take, lane);
+  } else {
+    // more survivors than the buffer holds: batches of 128, each ranked together with the best-k so far
+    // (cost grows linearly with the size of the near-tie cluster instead of falling off a cliff)
+    __threadfence_block();
+    take = 0;
+    for (int base = 0; base < ns; base += 128) {
+      const int nb = min(128, ns - base);
+      for (int u = lane; u < nb; u += 32) sm.keys[u] = (unsigned long long)(uint32_t)__ldcg(&list[base + u].x);
+      __syncwarp();
+      rescore_rows(sm, nb, key_pm, CK, qq, inv_sqrt_ck, lane);
+      for (int u = lane; u < take; u += 32) sm.keys[nb + u] = sm.sel[u];
+      __syncwarp();
+      const int total = nb + take;
+      take = min(top_k, total);
+      rank_into_sel(sm, total, take, lane);
     }
   }
   __syncwarp();
