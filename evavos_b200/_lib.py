@@ -12,7 +12,7 @@ import threading
 
 ABI_VERSION = 2
 F32, BF16 = 0, 1
-PATH_AUTO, PATH_TENSOR, PATH_SIMT = 0, 1, 2
+PATH_AUTO, PATH_TENSOR, PATH_SIMT, PATH_TENSOR_DENSE = 0, 1, 2, 3
 TILE_POS = 128
 TILE_BYTES = 20480
 MAX_TOPK = 128
@@ -67,6 +67,7 @@ SIGNATURES = {
                                           _c_i64, _c_i64, _c_vp]),
     "evavos_memread_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(MemReadArgs)]),
     "evavos_memread": (_c_i32, [ctypes.POINTER(MemReadArgs), _c_vp]),
+    "evavos_memread_overflow_count": (_c_i32, [ctypes.POINTER(MemReadArgs), ctypes.POINTER(ctypes.c_uint32), _c_vp]),
     "evavos_readout": (_c_i32, [ctypes.POINTER(BankShadow), _c_vp, _c_vp, _c_i64, _c_i32, _c_vp, _c_i64, _c_i64, _c_vp]),
     "evavos_readout_qmajor": (_c_i32, [ctypes.POINTER(BankShadow), _c_vp, _c_vp, _c_i64, _c_i32, _c_vp, _c_vp]),
     "evavos_peer_enable": (_c_i32, [_c_i32]),

@@ -76,7 +76,9 @@ Carve carve_workspace(const EvavosMemReadArgs& a, int n_chunks, int n_sm, uint8_
   c.sb.cand_cnt = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * nq_pad));
   c.sb.cand = reinterpret_cast<int2*>(take(sizeof(int2) * nq_pad * kCandCap));
   c.sb.strip = take(n_chunks > 0 ? score_pass_strip_bytes(a.n_query, n_chunks, n_sm) : 0);
-  c.sb.grid_counter = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * (size_t)mt));
+  c.sb.grid_counter = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * (size_t)(mt + 1)));
+  c.sb.overflow_cnt = c.sb.grid_counter ? c.sb.grid_counter + mt : nullptr;
+  c.sb.overflow_list = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * nq_pad));
   c.idx = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * a.n_query * a.top_k));
   c.weight = reinterpret_cast<float*>(take(sizeof(float) * a.n_query * a.top_k));
   c.total = off + 1024;  // slack for aligning the caller's pointer
@@ -124,7 +126,8 @@ int validate_read(const EvavosMemReadArgs* a) {
     set_error("selected index k out of range (THW=%lld < top_k=%d)", (long long)a->n_pos, a->top_k);
     return EVAVOS_ERR_TOPK_RANGE;
   }
-  if (a->path == EVAVOS_PATH_TENSOR && !(a->bank.CK == 64 && a->bank.key_tiles && a->bank.key_maxnorm)) {
+  if ((a->path == EVAVOS_PATH_TENSOR || a->path == EVAVOS_PATH_TENSOR_DENSE) &&
+      !(a->bank.CK == 64 && a->bank.key_tiles && a->bank.key_maxnorm)) {
     set_error("tensor path needs CK == 64, key_tiles and key_maxnorm");
     return EVAVOS_ERR_UNSUPPORTED;
   }
@@ -198,6 +201,45 @@ size_t evavos_memread_workspace_bytes(const EvavosMemReadArgs* args) {
   const int chunks = use_tensor_path(*args) ? score_pass_chunks(args->n_pos, args->n_query, n_sm) : 0;
   return carve_workspace(*args, chunks, n_sm, nullptr).total;
 }
+
+// ---- overflow hint: does the exact tiled pass (select_dense.cu) have anything to do? ---------------------------------
+// Its launch costs ~2 us of every read even when no list overflowed - the normal case.  The finalizer therefore sets
+// a word of mapped host memory whenever it meets an overflowed query; a read launches the tiled pass only if one of
+// the previous 64 reads on this device left the word set (or the caller asks with EVAVOS_PATH_TENSOR_DENSE).
+// Without the pass the finalizer redoes an overflowed query itself (one warp, whole bank): the hint only ever trades
+// speed, never the result.  Races between host threads on the word are harmless for the same reason.
+namespace {
+struct OverflowHint {
+  volatile uint32_t* host;
+  uint32_t* dev;
+  bool tried;
+  int sticky;   // reads left for which the pass is launched after the word was last seen set: a wrong launch costs
+                // 2 us, a wrong skip a query redone by one warp (~0.3 ms), so one overflow buys the pass 64 reads
+};
+OverflowHint g_hint[64];
+
+OverflowHint* overflow_hint() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  OverflowHint& h = g_hint[dev];
+  if (!h.tried) {
+    h.tried = true;
+    void* hp = nullptr;
+    void* dp = nullptr;
+    if (cudaHostAlloc(&hp, 64, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+      if (cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
+        h.host = reinterpret_cast<volatile uint32_t*>(hp);
+        h.dev = reinterpret_cast<uint32_t*>(dp);
+        *h.host = 0;
+      } else {
+        cudaFreeHost(hp);
+      }
+    }
+    (void)cudaGetLastError();
+  }
+  return h.host ? &h : nullptr;
+}
+}  // namespace
 
 // ---- optional per-stage timing of evavos_memread (diagnostics; CUDA events on the caller's stream) ----------
 // A ring of event sets, one per evavos_memread call, so that a timed loop needs no synchronisation between calls;
@@ -285,12 +327,35 @@ int evavos_memread(const EvavosMemReadArgs* a, evavos_stream_t stream) {
   stage_mark(1, st);   // (stage 1, the round-1 exact fallback launch, no longer exists: always ~0)
   stage_mark(2, st);
 
-  // 2. tightening of the list (tensor path), exact rescoring, top-k, softmax; a query whose list overflowed
-  //    (massive ties) is redone exactly inside the same kernel
+  // 2. tightening of the list (tensor path), exact rescoring, top-k, softmax; a query whose list overflowed is
+  //    only recorded (tensor path) and finished by step 2b
+  bool dense_pass = false;
+  uint32_t* hint_dev = nullptr;
+  if (tensor) {
+    OverflowHint* h = overflow_hint();
+    if (h) {
+      if (*h->host != 0) {
+        h->sticky = 64;
+        *h->host = 0;   // the kernels of this and the following reads set it again if they meet an overflowed list
+      }
+      hint_dev = h->dev;
+    }
+    dense_pass = a->path == EVAVOS_PATH_TENSOR_DENSE || h == nullptr || h->sticky > 0;
+    if (h && h->sticky > 0) --h->sticky;
+  }
   rc = launch_finalize(a->bank.key_pm, a->query, a->query_ch_stride, CK, a->n_pos, a->n_query, a->top_k, c.sb.cand,
                        c.sb.cand_cnt, tensor ? 1 : 0, a->bank.key_maxnorm, idx, weight, a->topk_score, a->peers,
-                       a->peer_gather_offset, st);
+                       a->peer_gather_offset, dense_pass ? c.sb.overflow_list : nullptr,
+                       tensor ? c.sb.overflow_cnt : nullptr, hint_dev, st);
   if (rc) return rc;
+  // 2b. queries whose list overflowed (the filter cannot separate their candidates): exact tiled selection + the same
+  //     finalizer (see the overflow hint above for when it is launched)
+  if (dense_pass) {
+    rc = launch_overflow_exact(a->bank.key_pm, a->query, a->query_ch_stride, a->n_pos, a->n_query, a->top_k, c.sb.cand,
+                               c.sb.overflow_list, c.sb.overflow_cnt, a->bank.key_maxnorm, idx, weight, a->topk_score,
+                               a->peers, a->peer_gather_offset, n_sm, st);
+    if (rc) return rc;
+  }
   stage_mark(3, st);
 
   // 3. sparse readout for all objects
@@ -301,6 +366,24 @@ int evavos_memread(const EvavosMemReadArgs* a, evavos_stream_t stream) {
   }
   stage_mark(4, st);
   stage_done();
+  return EVAVOS_OK;
+}
+
+int evavos_memread_overflow_count(const EvavosMemReadArgs* a, uint32_t* count, evavos_stream_t stream) {
+  int rc = validate_read(a);
+  if (rc) return rc;
+  if (!count || !a->workspace) { set_error("overflow_count: NULL argument"); return EVAVOS_ERR_INVALID; }
+  *count = 0;
+  if (!use_tensor_path(*a)) return EVAVOS_OK;
+  int n_sm = 0;
+  if (a->n_sm > 0) n_sm = a->n_sm;
+  else if (device_sm_count(&n_sm)) n_sm = 148;
+  const int chunks = score_pass_chunks(a->n_pos, a->n_query, n_sm);
+  uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(a->workspace), 1024));
+  const Carve c = carve_workspace(*a, chunks, n_sm, base);
+  cudaStream_t st = (cudaStream_t)stream;
+  EVAVOS_CUDA_OK(cudaMemcpyAsync(count, c.sb.overflow_cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  EVAVOS_CUDA_OK(cudaStreamSynchronize(st));
   return EVAVOS_OK;
 }
 

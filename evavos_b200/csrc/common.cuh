@@ -114,7 +114,9 @@ struct SelectBuffers {
   int32_t* cand_cnt;  // [nq_pad]
   int2* cand;         // [nq_pad][kCandCap] (position, filter score bits; the exact SIMT selection leaves the score 0)
   void* strip;        // phase-B staging strips of the filter's epilogue threads (score_pass_strip_bytes)
-  unsigned int* grid_counter;
+  unsigned int* grid_counter;   // [MT + 1], zeroed by launch_score_select; the last word is overflow_cnt
+  int32_t* overflow_list;       // [nq_pad] queries whose list overflowed (written by the finalizer)
+  unsigned int* overflow_cnt;   // their number
 };
 
 // The query is always addressed in the caller's layout: element (c, q) at query[c * query_ch_stride + q].
@@ -125,7 +127,15 @@ int launch_brute_select(const float* key_pm, const float* query, int64_t query_c
 int launch_finalize(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_pos,
                     int64_t n_query, int top_k, const int2* cand, const int32_t* cand_cnt, int scored,
                     const float* key_maxnorm, int32_t* out_idx, float* out_weight, float* out_score,
-                    const EvavosPeers* peers, int64_t peer_gather_offset, cudaStream_t st);
+                    const EvavosPeers* peers, int64_t peer_gather_offset, int32_t* overflow_list,
+                    unsigned int* overflow_cnt, uint32_t* overflow_hint, cudaStream_t st);
+// Exact selection + finalization of the queries the finalizer listed as overflowed (select_dense.cu); a no-op
+// (one empty launch) when there are none.
+int launch_overflow_exact(const float* key_pm, const float* query, int64_t query_ch_stride, int64_t n_pos,
+                          int64_t n_query, int top_k, int2* cand, const int32_t* overflow_list,
+                          const unsigned int* overflow_cnt, const float* key_maxnorm, int32_t* out_idx,
+                          float* out_weight, float* out_score, const EvavosPeers* peers, int64_t peer_gather_offset,
+                          int n_sm, cudaStream_t st);
 size_t jf_workspace_bytes(int64_t T, int h, int w);
 int launch_jf_metrics(const uint8_t* pred, const uint8_t* gt, int64_t T, int h, int w, int radius, void* workspace,
                       double* out, int32_t* gt_empty, cudaStream_t st);

@@ -843,13 +843,18 @@ int score_pass_chunks(int64_t n_pos, int64_t n_query, int n_sm) {
 
 // Phase A contracts every R-th tile of a chunk.  The expected candidate count grows like ~1.26 k R (plus the error
 // margin) and every candidate costs the candidate pass a trip off its fast path, while the threshold pass shrinks
-// by 1/R.  Measured on B200 (filter time in us, R = 1 | 2 | 3 | 4):
-//   cfg2 (23 tiles per CTA)    43 | 46 | 55 | 59        cfg4 (230)  146 | 130 | 147 | 154       cfg5 (1 594)  804 | 688 | 758 | 790
-// so R = 2 once a CTA's chunk is long enough for the saved half sweep to outweigh the denser hits, else R = 1.
+// by 1/R.  What decides is the candidate DENSITY, ~1.8 k R / n_pos per (query, position): short banks are dense
+// whatever the chunk length.  Measured on B200 (scripts/stride_sweep.py, 480p maps; filter us at R = 1 | 2 | 3):
+//   positions   x 1 620 queries         x 8 100 queries (5 query frames per launch)
+//      32 400    42.9 |  46.0 |  49.7    133.0 | 148.7 | 171.0
+//      81 000    64.0 |  63.3 |  66.1    230.3 | 232.4 | 255.6
+//     162 000    93.6 |  86.6 |  89.0    377.8 | 356.4 | 372.8
+//     324 000   147.3 | 130.8 | 131.7    658.4 | 586.9 | 587.8        (cfg5, 408 000 x 8 160: 804 | 688 | 758)
+// so R = 2 from ~100 000 positions on, else R = 1.
 int score_pass_sample_stride(int64_t n_pos, int n_chunks, int requested) {
   const int64_t nt = ceil_div(n_pos, kTilePos);
   const int64_t per_cta = nt / (n_chunks > 0 ? n_chunks : 1);
-  int r = requested > 0 ? requested : (per_cta >= 64 ? 2 : 1);
+  int r = requested > 0 ? requested : (n_pos >= 98304 && per_cta >= 32 ? 2 : 1);
   if (r > 8) r = 8;
   const int64_t cap = nt / 48;       // the sample keeps >= ~48 tiles so that 128 classes over it say something
   if (r > cap) r = (int)cap;
@@ -919,7 +924,8 @@ int launch_score_select(const float* query, int64_t query_ch_stride, const void*
       p.flush_period = (int)period;
     }
     const unsigned grid = (unsigned)(p.n_mtiles * n_chunks);
-    EVAVOS_CUDA_OK(cudaMemsetAsync(grid_counter, 0, sizeof(unsigned int) * (size_t)p.n_mtiles, st));
+    // (all mt_total + 1 words: the word after the tile counters is the finalizer's overflow count, see api.cu)
+    EVAVOS_CUDA_OK(cudaMemsetAsync(grid_counter, 0, sizeof(unsigned int) * (size_t)(mt_total + 1), st));
     // cooperative (the grid barrier needs every CTA resident) and, with EVAVOS_CLUSTER = 2, in clusters of two
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);

@@ -199,7 +199,7 @@ __device__ __forceinline__ void rank_into_sel(FinalizeWarpSmem& sm, int n, int t
 // insertion only for scores that beat the current k-th (rare once the list has warmed up).  Same (score, position)
 // order as everything else.  This is the slow path of queries whose candidate list overflowed (thousands of
 // tied or nearly tied keys); returns the number of entries (min(top_k, n_pos)).
-__device__ __noinline__ int exact_topk_warp(FinalizeWarpSmem& sm, const float* __restrict__ key_pm, int CK,
+static __device__ __noinline__ int exact_topk_warp(FinalizeWarpSmem& sm, const float* __restrict__ key_pm, int CK,
                                             int64_t n_pos, int top_k, float qq, float inv_sqrt_ck, int lane) {
   int filled = 0;
   for (int64_t base = 0; base < n_pos; base += 32) {
@@ -266,7 +266,8 @@ __device__ __forceinline__ void finalize_query_warp(FinalizeWarpSmem& sm, int la
       ns = min(cnt_raw, kMaxSurvivors);
       for (int e = lane; e < ns; e += 32) sm.keys[e] = (unsigned long long)(uint32_t)__ldcg(&list[e].x);
     } else {
-      const float two_eps = 2.0f * filter_eps(sqrtf(qq), __ldg(key_maxnorm));
+      // scored == 2: the list carries EXACT scores (overflow_exact_kernel): the cut needs no error margin
+      const float two_eps = scored == 2 ? 0.f : 2.0f * filter_eps(sqrtf(qq), __ldg(key_maxnorm));
       const int k = min(top_k, cnt_raw);
       if (cnt_raw <= top_k + 32) {   // a list this short is not worth cutting: rescore all of it
         ns = cnt_raw;

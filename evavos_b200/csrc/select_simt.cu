@@ -189,15 +189,32 @@ __global__ void __launch_bounds__(32 * kFinWarps) finalize_kernel(
     const float* __restrict__ key_pm, const float* __restrict__ query, int64_t query_ch_stride, int CK, int64_t n_pos,
     int64_t n_query, int top_k, const int2* __restrict__ cand, const int32_t* __restrict__ cand_cnt, int scored,
     const float* __restrict__ key_maxnorm, int32_t* __restrict__ out_idx, float* __restrict__ out_weight,
-    float* __restrict__ out_score, const PeerPush push) {
+    float* __restrict__ out_score, const PeerPush push, int32_t* __restrict__ overflow_list,
+    unsigned int* __restrict__ overflow_cnt, uint32_t* __restrict__ overflow_hint) {
   __shared__ FinalizeWarpSmem sm[kFinWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * kFinWarps + warp;
   pdl_wait();
   pdl_launch_dependents();
   if (q >= n_query) return;
-  finalize_query_warp(sm[warp], lane, q, key_pm, query, query_ch_stride, CK, n_pos, top_k, cand, __ldcg(cand_cnt + q),
-                      scored, key_maxnorm, out_idx, out_weight, out_score, push, n_query);
+  const int cnt = __ldcg(cand_cnt + q);
+  if (cnt > kCandCap && overflow_cnt != nullptr) {
+    // more positions inside the filter's margin than a list holds.  Count it, tell the host (the next read will
+    // launch the tiled pass, api.cu) and, when that pass follows this kernel, leave the query to it:
+    // overflow_exact_kernel scores it exactly against the whole bank together with the other queries listed here.
+    // Otherwise this warp redoes it alone (finalize_query_warp's exact path).
+    unsigned int slot = 0;
+    if (lane == 0) {
+      slot = atomicAdd(overflow_cnt, 1u);
+      if (overflow_hint != nullptr) *reinterpret_cast<volatile uint32_t*>(overflow_hint) = 1u;
+    }
+    if (overflow_list != nullptr) {
+      if (lane == 0) overflow_list[slot] = (int32_t)q;
+      return;
+    }
+  }
+  finalize_query_warp(sm[warp], lane, q, key_pm, query, query_ch_stride, CK, n_pos, top_k, cand, cnt, scored,
+                      key_maxnorm, out_idx, out_weight, out_score, push, n_query);
 }
 
 }  // namespace
@@ -215,7 +232,8 @@ int launch_brute_select(const float* key_pm, const float* query, int64_t query_c
 int launch_finalize(const float* key_pm, const float* query, int64_t query_ch_stride, int CK, int64_t n_pos,
                     int64_t n_query, int top_k, const int2* cand, const int32_t* cand_cnt, int scored,
                     const float* key_maxnorm, int32_t* out_idx, float* out_weight, float* out_score,
-                    const EvavosPeers* peers, int64_t peer_gather_offset, cudaStream_t st) {
+                    const EvavosPeers* peers, int64_t peer_gather_offset, int32_t* overflow_list,
+                    unsigned int* overflow_cnt, uint32_t* overflow_hint, cudaStream_t st) {
   PeerPush push;
   memset(&push, 0, sizeof(push));
   if (peers != nullptr) {
@@ -226,7 +244,7 @@ int launch_finalize(const float* key_pm, const float* query, int64_t query_ch_st
   }
   EVAVOS_CUDA_OK(launch_pdl(finalize_kernel, dim3((unsigned)ceil_div(n_query, kFinWarps)), dim3(32 * kFinWarps), 0, st,
                             key_pm, query, query_ch_stride, CK, n_pos, n_query, top_k, cand, cand_cnt, scored,
-                            key_maxnorm, out_idx, out_weight, out_score, push));
+                            key_maxnorm, out_idx, out_weight, out_score, push, overflow_list, overflow_cnt, overflow_hint));
   return EVAVOS_OK;
 }
 

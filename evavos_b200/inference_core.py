@@ -27,6 +27,7 @@ import torch
 from .aggregate import aggregate_wbg, argmax_unpad
 from .memory_bank import MemoryBank
 from .memory_reader import EvalMemoryReader
+from .staging import download_numpy, upload
 from .tensor_util import pad_divide_by
 
 
@@ -40,9 +41,14 @@ class InferenceCore:
     """
 
     def __init__(self, prop_net, fuse_net, images, num_objects, mem_profile=0, mem_freq=5, device="cuda", *,
-                 amp=False):
-        """``amp`` (keyword of this engine, not of the reference): run the conv encoders / decoder under bf16 autocast
-        in channels_last; keys, values and the memory read stay fp32."""
+                 amp=False, fold_bn=True, channels_last=None, cuda_graphs=False):
+        """Keywords of this engine, not of the reference:
+        ``amp``: run the conv encoders / decoder under bf16 autocast; keys, values and the memory read stay fp32.
+        ``fold_bn``: run the two ResNet encoders through BatchNorm-folded copies (conv_opt.py; ``prop_net`` itself is
+        not modified; only with this package's PropagationNetwork).
+        ``channels_last``: NHWC conv stacks (default: same as ``amp``).
+        ``cuda_graphs``: capture the key encoder, decoder and value encoder once per input shape and replay them
+        (graphs.py; this package's PropagationNetwork only).  The graphs are cached on ``prop_net``."""
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("evavos_b200.InferenceCore needs a CUDA device: the memory read has no CPU path")
@@ -53,8 +59,12 @@ class InferenceCore:
         self.mem_freq = mem_freq
         self.device = dev
         self.amp = bool(amp)
-        if self.amp:
+        self.channels_last = self.amp if channels_last is None else bool(channels_last)
+        if self.channels_last:
             self.prop_net = self.prop_net.to(memory_format=torch.channels_last)
+        ours = hasattr(prop_net, "decode_input")
+        self.fold_bn = bool(fold_bn) and ours and not prop_net.training
+        self.cuda_graphs = bool(cuda_graphs) and ours
 
         if mem_profile == 0:
             self.data_dev, self.result_dev, self.k_buf_size, self.i_buf_size = dev, dev, 105, -1
@@ -70,6 +80,9 @@ class InferenceCore:
         h, w = images.shape[-2:]
         self.k = num_objects
 
+        if self.data_dev.type == "cuda" and not images.is_cuda:
+            # upload first, pad on the GPU (the reference pads 150 MB of frames on the host, inference_core.py:63)
+            images = upload(images, self.data_dev)
         self.images, self.pad = pad_divide_by(images, 16, images.shape[-2:])
         nh, nw = self.images.shape[-2:]
         self.images = self.images.to(self.data_dev, non_blocking=False)
@@ -129,16 +142,35 @@ class InferenceCore:
     def _autocast(self):
         return torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp)
 
+    @property
+    def _conv(self):
+        """The three conv passes under this engine's options (conv_opt.ConvPasses), resolved on first use and after a
+        deepcopy (policies deep-copy whole processors; captured graphs stay with the network they were made for)."""
+        c = self.__dict__.get("_conv_cache")
+        if c is None:
+            from .conv_opt import conv_passes
+            c = self.__dict__["_conv_cache"] = conv_passes(self.prop_net, self.amp, self.channels_last, self.fold_bn,
+                                                           self.cuda_graphs)
+        return c
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_conv_cache", None)
+        return state
+
     def _encode_key(self, frames):
-        with self._autocast():
-            outs = self.prop_net.encode_key(frames.contiguous(memory_format=torch.channels_last) if self.amp else frames)
-        # the memory key (and everything the read touches) stays fp32; the skip features keep the conv dtype
-        return (outs[0].float(),) + tuple(outs[1:]) if self.amp else outs
+        if hasattr(self.prop_net, "decode_input"):
+            return self._conv.encode_key(frames)
+        with self._autocast():      # a reference network passed in: its own encode_key, as it is
+            outs = self.prop_net.encode_key(frames.contiguous(memory_format=torch.channels_last)
+                                            if self.channels_last else frames)
+        return (outs[0].float(),) + tuple(outs[1:])
 
     def _encode_value(self, frame, qf16, masks):
+        if hasattr(self.prop_net, "decode_input"):
+            return self._conv.encode_value(frame, qf16, masks)
         with self._autocast():
-            v = self.prop_net.encode_value(frame, qf16, masks)
-        return v.float() if self.amp else v
+            return self.prop_net.encode_value(frame, qf16, masks).float()
 
     def _key_feats(self, frames):
         """Key features of several frames: the ones not cached yet go through the encoder as ONE batch (they only
@@ -228,9 +260,7 @@ class InferenceCore:
                 m4 = torch.empty((len(seg), K, 2 * CV, H, W), dtype=torch.float32, device=self.device)
                 self._read(bank, qk, out=m4 if len(seg) > 1 else m4[0])
                 m4[:, :, CV:] = torch.cat([f[1] for f in feats], 0).unsqueeze(1)
-                with self._autocast():
-                    decoded = self.prop_net.decode_input(m4, torch.cat([f[3] for f in feats], 0),
-                                                         torch.cat([f[4] for f in feats], 0)).float()
+                decoded = self._conv.decode(m4, torch.cat([f[3] for f in feats], 0), torch.cat([f[4] for f in feats], 0))
             else:
                 readout, _ = self._read(bank, qk)
                 if len(seg) == 1:
@@ -292,5 +322,5 @@ class InferenceCore:
 
         # all frames, argmax + un-padding in one kernel (the reference loops T argmax calls and slices, :247-257)
         self.masks, unpadded = argmax_unpad(self.prob, self.pad, self.h, self.w)
-        self.np_masks = unpadded.cpu().numpy()
+        self.np_masks = download_numpy(unpadded)
         return self.np_masks

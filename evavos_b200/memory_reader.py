@@ -146,6 +146,7 @@ def memory_read(bank: MemoryBank, qk: torch.Tensor, top_k: int = 50, n_frames: i
         ws = _workspace.get(dev, need)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         _lib.check(lib.evavos_memread(ctypes.byref(a), _lib.current_stream_ptr(dev)))
+    _last_read[0] = (a, dev, q2, ws)
     aff = TopKAffinity(idx, weight, score, n_pos, bank.H, bank.W) if want_topk else None
     if want_readout:
         if user_out is None:
@@ -155,6 +156,21 @@ def memory_read(bank: MemoryBank, qk: torch.Tensor, top_k: int = 50, n_frames: i
     else:
         out = None
     return out, aff
+
+
+_last_read = [None]
+
+
+def last_overflow_count() -> int:
+    """Diagnostics: the number of queries of the most recent ``memory_read`` whose candidate list overflowed and that
+    were therefore selected by the exact tiled pass (evavos_memread_overflow_count).  Synchronises the stream."""
+    if _last_read[0] is None:
+        raise RuntimeError("no memory_read has run yet")
+    a, dev, _, _ = _last_read[0]
+    n = ctypes.c_uint32(0)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().evavos_memread_overflow_count(ctypes.byref(a), ctypes.byref(n), _lib.current_stream_ptr(dev)))
+    return int(n.value)
 
 
 class EvalMemoryReader(nn.Module):

@@ -223,22 +223,29 @@ class PropagationNetwork(nn.Module):
         self.memory = EvalMemoryReader(top_k, km=None)
         self.attn_memory = AttentionMemory(top_k)
         self.decoder = Decoder()
+        self._others_idx = {}
 
-    def encode_value(self, frame, kf16, masks):
-        """frame (1,3,h,w), kf16 (1,1024,H,W), masks (K,1,h,w) -> (K,512,1,H,W) (prop_net.py:153-170)."""
+    def encode_value(self, frame, kf16, masks, value_encoder=None):
+        """frame (1,3,h,w), kf16 (1,1024,H,W), masks (K,1,h,w) -> (K,512,1,H,W) (prop_net.py:153-170).
+        ``value_encoder``: a stand-in for ``self.value_encoder`` (the BatchNorm-folded copy of conv_opt.py)."""
         k, _, h, w = masks.shape
         frame = frame.view(1, 3, h, w).expand(k, -1, -1, -1)
         kf16 = kf16.expand(k, -1, -1, -1)
         if k != 1:
-            # per object, the sum of every OTHER object's mask (summed in index order, like the reference)
-            keep = ~torch.eye(k, dtype=torch.bool, device=masks.device)
-            others = torch.stack([masks[keep[i]].sum(0) for i in range(k)], 0)
+            # per object, the sum of every OTHER object's mask (summed in index order, like the reference); gathered
+            # with a cached index tensor: boolean indexing would synchronise (and cannot be captured in a CUDA graph)
+            key = (k, masks.device)
+            idx = self._others_idx.get(key)
+            if idx is None:
+                idx = torch.tensor([[j for j in range(k) if j != i] for i in range(k)], device=masks.device)
+                self._others_idx[key] = idx
+            others = masks[:, 0][idx].sum(1).unsqueeze(1)
         else:
             others = torch.zeros_like(masks)
-        return self.value_encoder(frame, kf16, masks, others).unsqueeze(2)
+        return (value_encoder or self.value_encoder)(frame, kf16, masks, others).unsqueeze(2)
 
-    def encode_key(self, frame):
-        f16, f8, f4 = self.key_encoder(frame)
+    def encode_key(self, frame, key_encoder=None):
+        f16, f8, f4 = (key_encoder or self.key_encoder)(frame)
         return self.key_proj(f16), self.key_comp(f16), f16, f8, f4
 
     def read_memory(self, mk16, mv16, qk16):

@@ -82,7 +82,11 @@ extern "C" {
 
 #define EVAVOS_PATH_AUTO 0   /* tcgen05 filter when CK == 64, else SIMT                      */
 #define EVAVOS_PATH_TENSOR 1 /* tcgen05/TMEM candidate filter + exact fp32 rescoring          */
-#define EVAVOS_PATH_SIMT 2   /* exact fp32 CUDA-core radix select (also the overflow path)    */
+#define EVAVOS_PATH_SIMT 2   /* exact fp32 CUDA-core radix select                             */
+#define EVAVOS_PATH_TENSOR_DENSE 3 /* TENSOR, and the exact tiled pass for overflowed lists is always launched.
+                                      AUTO / TENSOR launch it only when the previous read on this device saw an
+                                      overflow (a host-visible hint the kernels set; until then an overflowed query
+                                      is redone by one warp inside the finalizer: same result, slower)          */
 
 #define EVAVOS_TILE_POS 128      /* memory positions per key tile image  */
 #define EVAVOS_TILE_BYTES 20480  /* 128 rows x 128 B (bf16 keys, CK=64) + 128 rows x 32 B (-|k|^2/2) */
@@ -183,6 +187,12 @@ int evavos_bank_write_values(const EvavosBankShadow* bank, const float* src, int
 
 size_t evavos_memread_workspace_bytes(const EvavosMemReadArgs* args);
 int evavos_memread(const EvavosMemReadArgs* args, evavos_stream_t stream);
+/*
+ * Diagnostics: how many queries of the LAST evavos_memread that ran with these arguments (same workspace, sizes and
+ * path) had more candidates inside the filter's error margin than a list holds and were selected by the exact tiled
+ * pass instead (select_dense.cu).  Synchronises `stream`.  0 on the SIMT path.  No reference counterpart.
+ */
+int evavos_memread_overflow_count(const EvavosMemReadArgs* args, uint32_t* count, evavos_stream_t stream);
 
 /* Sparse readout: out[o][c][q] = sum_j weight[q][j] * val_pm[o][idx[q][j]][c]; idx < 0 entries are skipped. */
 int evavos_readout(const EvavosBankShadow* bank, const int32_t* idx, const float* weight, int64_t n_query,

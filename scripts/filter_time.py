@@ -27,7 +27,7 @@ for name in (sys.argv[1:] or ["cfg1", "cfg2", "cfg4"]):
     lib.evavos_stage_timing(1)
     acc, reps = np.zeros(4), 20
     for i in range(reps + 3):
-        ev.memory_read(bank, qk, 50)
+        ev.memory_read(bank, qk, 50, path=int(os.environ.get("FILTER_PATH", 0)))
         ms = (ctypes.c_float * 4)()
         lib.evavos_stage_timing_read(ms)
         if i >= 3:

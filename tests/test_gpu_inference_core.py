@@ -116,3 +116,39 @@ def test_bf16_channels_last_convs_agree_with_fp32():
     decided = decided[:, lh:decided.shape[1] - uh or None, lw:decided.shape[2] - uw or None]
     assert ((ma != mb) & decided).mean() < 1e-3
     assert agree > 0.97
+
+
+@pytest.mark.parametrize("tag,opts", [
+    ("e2e_k1", dict(fold_bn=False)),
+    ("e2e_k2", dict(channels_last=True)),
+    ("e2e_k2", dict(cuda_graphs=True)),
+    ("e2e_k1", dict(cuda_graphs=True, channels_last=True)),
+])
+def test_engine_options_do_not_change_the_result(tag, opts):
+    """BatchNorm folding + fused cuDNN conv-bias-ReLU (default), NHWC and CUDA-graph replay of the conv passes are
+    re-orderings of the same arithmetic: probabilities agree to fp32 rounding with the plain engine, and with the
+    reference's golden output."""
+    import evavos_b200 as ev
+    g = load(f"{tag}.npz")
+    prop, fuse = _nets()
+    images = torch.from_numpy(g["images"])
+    k = int(g["num_objects"])
+    plain = ev.InferenceCore(prop, fuse, images, k, mem_freq=int(g["mem_freq"]), device="cuda:0", fold_bn=False)
+    tuned = ev.InferenceCore(prop, fuse, images, k, mem_freq=int(g["mem_freq"]), device="cuda:0", **opts)
+    for i in range(int(g["n_interactions"])):
+        mask, frame, scribble = torch.from_numpy(g[f"mask_{i}"]), int(g[f"frame_{i}"]), bool(g[f"scribble_{i}"])
+        ma, mb = plain.interact(mask, frame, scribble=scribble), tuned.interact(mask, frame, scribble=scribble)
+        assert (plain.prob - tuned.prob).abs().max().item() < 1e-3
+        assert (ma != mb).mean() < 1e-3
+        assert np.abs(tuned.prob.cpu().numpy() - g[f"prob_{i}"]).max() < 2e-3
+    if opts.get("cuda_graphs"):
+        # a second video through the same network replays the captured graphs; a deep copy of the processor
+        # (interactions/policies.py:103) gets its own
+        again = ev.InferenceCore(prop, fuse, images, k, mem_freq=int(g["mem_freq"]), device="cuda:0", **opts)
+        mask, frame = torch.from_numpy(g["mask_0"]), int(g["frame_0"])
+        first = ev.InferenceCore(prop, fuse, images, k, mem_freq=int(g["mem_freq"]), device="cuda:0", fold_bn=False)
+        m1 = first.interact(mask, frame, scribble=bool(g["scribble_0"]))
+        m2 = again.interact(mask, frame, scribble=bool(g["scribble_0"]))
+        assert (first.prob - again.prob).abs().max().item() < 1e-3 and (m1 != m2).mean() < 1e-3
+        clone = copy.deepcopy(again)
+        assert torch.equal(clone.prob, again.prob)
