@@ -44,7 +44,7 @@ class MemoryBank:
             self.keys = None
             self.values = None
         self.key_pm = torch.empty((cap, self.CK), dtype=torch.float32, device=dev)
-        n_tile_bytes = ((cap + _lib.TILE_POS - 1) // _lib.TILE_POS) * _lib.TILE_BYTES
+        n_tile_bytes = int(_lib.load().evavos_key_tiles_bytes(cap))
         self.key_tiles = torch.empty((n_tile_bytes,), dtype=torch.uint8, device=dev) if self.CK == 64 else None
         self.key_maxnorm = torch.zeros((1,), dtype=torch.float32, device=dev)
         self.val_pm = torch.empty((self.K, cap, self.CV), dtype=value_dtype, device=dev) if self.K > 0 else None
