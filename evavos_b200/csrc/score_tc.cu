@@ -641,21 +641,29 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
     // visit(i, math): wait for accumulator tile i, read this warp's 64 columns as two 32-column blocks (the stage
     // goes back to the MMA warp as soon as the second block is in registers) and call
     // math(block, values, first position, number of valid columns).
-    auto visit = [&](int i, auto&& math) {
-      const int a = i % kAccStages;
-      mbar_wait(bar_acc_full + 8 * a, (uint32_t)((i / kAccStages) & 1));
+    // The loop state that depends on the iteration (accumulator stage, barrier parity, first position) is carried
+    // incrementally in 32-bit registers: at ~2.4 clk of tile time per instruction of a warp's visit
+    // (profiles/r2_filter_experiments.md) the divisions and 64-bit address arithmetic of `i % 3`, `i / 3` and
+    // tile_of(i) * 128 were worth ~10 % of the kernel.
+    // (pinned in registers: left alone, the compiler re-derives the shared-memory window and the TMEM address from
+    //  special registers in every iteration - 10 instructions per visit)
+    uint32_t ld_base = lane_addr + (uint32_t)colbase;
+    uint32_t acc_full0 = bar_acc_full, acc_empty0 = bar_acc_empty;
+    asm volatile("" : "+r"(ld_base), "+r"(acc_full0), "+r"(acc_empty0));
+    const int n_pos32 = (int)p.n_pos;   // n_pos < 2^31 (validate_read)
+    auto visit = [&](int i, int a, uint32_t ph, int n_first, auto&& math) {
+      mbar_wait(acc_full0 + 8 * a, ph);
       tc_fence_after();
       if (threadIdx.x == kEpiLeader) EVAVOS_TR(3, i);
       if constexpr ((EVAVOS_EXP & 32) != 0) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * a);
+        if (lane == 0) mbar_arrive(acc_empty0 + 8 * a);
       }
-      const int64_t n_first = (int64_t)tile_of(i) * kTilePos + colbase;
 #pragma unroll
       for (int blk = 0; blk < 2; ++blk) {
         float v[kCols];
         if constexpr (!(EVAVOS_EXP & 1)) {
-          tmem_ld32(lane_addr + (uint32_t)(a * 128 + colbase + blk * kCols), v);
+          tmem_ld32(ld_base + (uint32_t)(a * 128 + blk * kCols), v);
           tmem_ld_wait();
         } else {
 #pragma unroll
@@ -664,12 +672,12 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
         if (blk == 1 && !(EVAVOS_EXP & 32)) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * a);  // registers hold the tile: release the TMEM stage
+          if (lane == 0) mbar_arrive(acc_empty0 + 8 * a);  // registers hold the tile: release the TMEM stage
           if (threadIdx.x == kEpiLeader) EVAVOS_TR(4, i);
         }
-        const int64_t n0 = n_first + blk * kCols;
+        const int n0 = n_first + blk * kCols;
         if constexpr (!(EVAVOS_EXP & 2)) {
-          const int64_t left = p.n_pos - n0;
+          const int left = n_pos32 - n0;
           if (left < kCols) {   // rows of the bank's last tile at or beyond n_pos hold no position (warp-uniform)
 #pragma unroll
             for (int j = 0; j < kCols; ++j) v[j] = (j < left) ? v[j] : -INFINITY;
@@ -688,12 +696,22 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
       float cmax[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) cmax[j] = kEmptyNh;
-      for (int i = grp; i < n_sample; i += 2)
-        visit(i, [&](int blk, const float* v, int64_t) {
+      int a = grp % kAccStages;
+      uint32_t ph = (uint32_t)((grp / kAccStages) & 1);
+      int n_first = (t0 + grp * R) * kTilePos + colbase;
+      for (int i = grp; i < n_sample; i += 2) {
+        visit(i, a, ph, n_first, [&](int blk, const float* v, int) {
 #pragma unroll
           for (int j = 0; j < kCols / 2; ++j)
             cmax[blk * 16 + j] = fmaxf(fmaxf(cmax[blk * 16 + j], v[j]), v[j + kCols / 2]);
         });
+        n_first += 2 * R * kTilePos;
+        a += 2;
+        if (a >= kAccStages) {
+          a -= kAccStages;
+          ph ^= 1u;
+        }
+      }
       float4* dst = reinterpret_cast<float4*>(p.class_max + ((int64_t)chunk * p.nq_pad + q) * 128 + (ew >> 2) * 32);
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4)
@@ -750,30 +768,32 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
       };
       const int i_b0 = n_sample + (((n_sample & 1) == grp) ? 0 : 1);
       int since_flush = 0;
+      int a = i_b0 % kAccStages;
+      uint32_t ph = (uint32_t)((i_b0 / kAccStages) & 1);
+      int n0 = (t0 + (i_b0 - n_sample)) * kTilePos + colbase;   // first of this warp's 64 positions of tile i
       for (int i = i_b0; i < n_iter; i += 2) {
         // Both 32-column blocks are pulled out of TMEM before any math, so the accumulator stage goes back to the
         // MMA warp at once: a warp that has to stage hits must not hold up its group's release of the stage.
-        const int a = i % kAccStages;
-        mbar_wait(bar_acc_full + 8 * a, (uint32_t)((i / kAccStages) & 1));
+        mbar_wait(acc_full0 + 8 * a, ph);
         tc_fence_after();
         if (threadIdx.x == kEpiLeader) EVAVOS_TR(3, i);
         if constexpr ((EVAVOS_EXP & 32) != 0) {
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * a);
+          if (lane == 0) mbar_arrive(acc_empty0 + 8 * a);
         }
         float vv[2 * kCols];
         float* v0 = vv;
         float* v1 = vv + kCols;
         if constexpr (!(EVAVOS_EXP & 1)) {
 #ifdef EVAVOS_LD64
-          tmem_ld64(lane_addr + (uint32_t)(a * 128 + colbase), vv);   // one 64-column load instead of two of 32
+          tmem_ld64(ld_base + (uint32_t)(a * 128), vv);   // one 64-column load instead of two of 32
 #elif defined(EVAVOS_SEQLD)
-          tmem_ld32(lane_addr + (uint32_t)(a * 128 + colbase), v0);   // experiment: one load in flight per warp
+          tmem_ld32(ld_base + (uint32_t)(a * 128), v0);   // experiment: one load in flight per warp
           tmem_ld_wait();
-          tmem_ld32(lane_addr + (uint32_t)(a * 128 + colbase + kCols), v1);
+          tmem_ld32(ld_base + (uint32_t)(a * 128 + kCols), v1);
 #else
-          tmem_ld32(lane_addr + (uint32_t)(a * 128 + colbase), v0);
-          tmem_ld32(lane_addr + (uint32_t)(a * 128 + colbase + kCols), v1);
+          tmem_ld32(ld_base + (uint32_t)(a * 128), v0);
+          tmem_ld32(ld_base + (uint32_t)(a * 128 + kCols), v1);
 #endif
           tmem_ld_wait();
         } else {
@@ -783,12 +803,11 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
         if constexpr (!(EVAVOS_EXP & 32)) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * a);
+          if (lane == 0) mbar_arrive(acc_empty0 + 8 * a);
         }
         if (threadIdx.x == kEpiLeader) EVAVOS_TR(4, i);
         if constexpr (!(EVAVOS_EXP & 2)) {
-          const int64_t n0 = (int64_t)tile_of(i) * kTilePos + colbase;
-          const int64_t left = p.n_pos - n0;
+          const int left = n_pos32 - n0;
           if (left < 2 * kCols) {   // the bank's last tile: rows at or beyond n_pos hold no position (warp-uniform)
 #pragma unroll
             for (int j = 0; j < kCols; ++j) {
@@ -796,8 +815,8 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
               v1[j] = (j + kCols < left) ? v1[j] : -INFINITY;
             }
           }
-          block(v0, (int32_t)n0);
-          block(v1, (int32_t)n0 + kCols);
+          block(v0, n0);
+          block(v1, n0 + kCols);
           // every thread of the CTA resolves its strip on the same visit; a thread whose strip could not take the 8
           // groups of another visit resolves at once (so `overflow` cannot happen; ~1e-6 per thread and period)
           if (++since_flush >= p.flush_period || pending > kStrip - 8) {
@@ -808,6 +827,12 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
           }
         }
         if (threadIdx.x == kEpiLeader) EVAVOS_TR(5, i);
+        n0 += 2 * kTilePos;
+        a += 2;
+        if (a >= kAccStages) {
+          a -= kAccStages;
+          ph ^= 1u;
+        }
       }
       if (pending > 0 || overflow) flush_strip(ss, sp, pending, overflow, thr, p.cand, p.cand_cnt, q);
       if (threadIdx.x == kEpiLeader) EVAVOS_TR_MARK(58);
