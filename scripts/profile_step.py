@@ -3,6 +3,7 @@
     python scripts/profile_step.py [cfg2 cfg4 cfg5 extras]
 cfg2 / cfg4 / cfg5: bank append (write_keys / write_values), fused read (score_select, finalize, readout), aggregate.
 extras: attention read at 68x120, sharded merge on gathered lists, J&F metric at 480x854, argmax/unpad.
+dense: near-constant keys, every list overflows -> overflow_exact_kernel.
 """
 import os
 import sys
@@ -38,6 +39,22 @@ for name in names:
         for _ in range(2):
             ev.argmax_unpad(prob, (5, 5, 0, 0), 480, 854)
         torch.cuda.synchronize()
+        continue
+    if name == "dense":
+        # near-constant keys (what random-weight networks produce): every candidate list overflows and the exact tiled
+        # pass (overflow_exact_kernel) selects for all 8 100 queries of a 5-frame read against a 5-frame bank
+        from evavos_b200 import _lib
+        g = torch.Generator(device=dev).manual_seed(5)
+        t, h, w = 5, 30, 54
+        base = torch.randn(1, 64, 1, 1, 1, generator=g, device=dev)
+        bank = ev.MemoryBank(1, 64, 512, h, w, t, dev, keep_reference_layout=False)
+        bank.write_frames(0, base + 1e-3 * torch.randn(1, 64, t, h, w, generator=g, device=dev),
+                          torch.randn(1, 512, t, h, w, generator=g, device=dev))
+        qk = 0.9 * base + 1e-3 * torch.randn(1, 64, 5, h, w, generator=g, device=dev)
+        for _ in range(3):
+            ev.memory_read(bank, qk, TOP_K, path=_lib.PATH_TENSOR_DENSE)
+        torch.cuda.synchronize()
+        print(name, "done", flush=True)
         continue
     ck, cv, t, h, w, k, seed, _ = WORKLOADS[name]
     bf16 = name == "cfg5"
