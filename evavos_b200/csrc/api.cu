@@ -562,7 +562,7 @@ int evavos_topk_merge(const int32_t* cand_idx, const float* cand_score, int64_t 
                       int32_t top_k, int32_t shard, int32_t n_shards, int64_t pos_per_frame, int32_t* out_idx,
                       float* out_weight, float* out_score, int32_t* local_idx, evavos_stream_t stream) {
   if (!cand_idx || !cand_score || n_query <= 0 || n_cand <= 0 || top_k <= 0 || top_k > EVAVOS_MAX_TOPK ||
-      n_shards <= 0 || shard < 0 || shard >= n_shards || pos_per_frame <= 0) {
+      n_shards <= 0 || shard < 0 || shard >= n_shards || pos_per_frame <= 0 || pos_per_frame > 0x7fffffff) {
     set_error("topk_merge: bad arguments");
     return EVAVOS_ERR_INVALID;
   }
@@ -574,7 +574,7 @@ int evavos_topk_merge_gathered(const int32_t* gathered, int64_t n_query, int32_t
                                int32_t shard, int32_t n_shards, int64_t pos_per_frame, int32_t* out_idx,
                                float* out_weight, float* out_score, int32_t* local_idx, evavos_stream_t stream) {
   if (!gathered || n_query <= 0 || per_shard <= 0 || top_k <= 0 || top_k > EVAVOS_MAX_TOPK || n_shards <= 0 ||
-      shard < 0 || shard >= n_shards || pos_per_frame <= 0) {
+      shard < 0 || shard >= n_shards || pos_per_frame <= 0 || pos_per_frame > 0x7fffffff) {
     set_error("topk_merge_gathered: bad arguments");
     return EVAVOS_ERR_INVALID;
   }

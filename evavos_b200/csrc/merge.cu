@@ -29,18 +29,19 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(
   unsigned long long* sel = smem_keys + (size_t)4 * n_cand + (size_t)warp * EVAVOS_MAX_TOPK;
   int live = 0;
   const int per_shard = n_cand / n_shards;
+  const uint32_t ppf = (uint32_t)pos_per_frame;   // positions fit int32 (the merged indices are int32): 32-bit division
   for (int c = lane; c < n_cand; c += 32) {
     int64_t n;
     float sc;
     if constexpr (GATHERED) {
       const int src = c / per_shard, j = c - src * per_shard;
-      const int32_t* e = cand_idx + (((int64_t)src * n_query + q) * per_shard + j) * 2;
-      const int32_t loc = e[0];
-      sc = __int_as_float(e[1]);
+      const int2 e = *reinterpret_cast<const int2*>(cand_idx + (((int64_t)src * n_query + q) * per_shard + j) * 2);
+      const int32_t loc = e.x;
+      sc = __int_as_float(e.y);
       n = -1;
       if (loc >= 0) {
-        const int64_t frame = loc / pos_per_frame, r = loc - frame * pos_per_frame;
-        n = (frame * n_shards + src) * pos_per_frame + r;
+        const uint32_t frame = (uint32_t)loc / ppf, r = (uint32_t)loc - frame * ppf;
+        n = (int64_t)((frame * (uint32_t)n_shards + (uint32_t)src) * ppf + r);
       }
     } else {
       n = cand_idx[q * n_cand + c];
@@ -62,18 +63,17 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(
     // list heads: lane s owns list s, one warp-wide max and one pointer advance per output.
     int ptr = 0;
     unsigned long long head = lane < n_shards ? keys[lane * per_shard] : 0ull;
+    // (64-bit maximum as two 32-bit warp reductions - score bits, then position bits among the lanes that hold the
+    //  best score: 2 REDUX instead of 5 x (2 SHFL + a 64-bit compare); the kernel is instruction-bound)
     for (int j = 0; j < take; ++j) {
-      unsigned long long best = head;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-        best = other > best ? other : best;
-      }
-      if (head == best && best != 0ull) {  // keys are unique: exactly one lane advances
+      const uint32_t hi = (uint32_t)(head >> 32), lo = (uint32_t)head;
+      const uint32_t best_hi = __reduce_max_sync(0xffffffffu, hi);
+      const uint32_t best_lo = __reduce_max_sync(0xffffffffu, hi == best_hi ? lo : 0u);
+      if (hi == best_hi && lo == best_lo && head != 0ull) {  // keys are unique: exactly one lane advances
         ++ptr;
         head = ptr < per_shard ? keys[lane * per_shard + ptr] : 0ull;
       }
-      if (lane == 0) sel[j] = best;
+      if (lane == 0) sel[j] = ((unsigned long long)best_hi << 32) | (unsigned long long)best_lo;
     }
     __syncwarp();
   } else {
@@ -118,8 +118,9 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(
     if (local_idx) {
       int32_t loc = -1;
       if (ok) {
-        const int64_t frame = pos / pos_per_frame, r = pos % pos_per_frame;
-        if (frame % n_shards == shard) loc = (int32_t)((frame / n_shards) * pos_per_frame + r);
+        const uint32_t frame = (uint32_t)pos / ppf, r = (uint32_t)pos - frame * ppf;
+        const uint32_t lf = frame / (uint32_t)n_shards;
+        if (frame - lf * (uint32_t)n_shards == (uint32_t)shard) loc = (int32_t)(lf * ppf + r);
       }
       local_idx[o] = loc;
     }

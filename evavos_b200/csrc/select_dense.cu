@@ -79,9 +79,10 @@ __global__ void __launch_bounds__(kOvThreads, 2) overflow_exact_kernel(
 
   const float inv_sqrt_ck = 1.0f / sqrtf(64.0f);
   const int64_t n_blocks = (n_pos + kOvP - 1) / kOvP;
-  // pass 1 samples every 2nd / 4th block once the sample still fills every class >= 16 times (the list then gets
-  // ~1.3 k sample entries, far below kCandCap for k <= 64)
-  const int sample = top_k > 64 ? 1 : (n_blocks >= 64 ? 4 : (n_blocks >= 32 ? 2 : 1));
+  // pass 1 samples every 2nd / 4th block once the sample still fills every class >= 4 times: the bound is the
+  // ~1.3 k-th best of the sample, so the list gets ~1.3 k sample entries whatever the bank length (k <= 64: <= 333,
+  // far below kCandCap)
+  const int sample = top_k > 64 ? 1 : (n_blocks >= 16 ? 4 : (n_blocks >= 8 ? 2 : 1));
 
   for (int tile = blockIdx.x; tile * kOvQ < n_over; tile += gridDim.x) {
     __syncthreads();   // the previous tile's finalizer scratch aliases the tiles

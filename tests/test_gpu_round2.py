@@ -239,12 +239,14 @@ def test_argmax_nan_and_many_objects_attention():
     assert (got.double() - ref).abs().max().item() < 2e-6
 
 
-@pytest.mark.parametrize("t,frames,noise", [(6, 1, 2e-3), (3, 2, 1e-3), (7, 3, 5e-4)])
-def test_near_constant_keys_take_the_exact_tiled_pass(t, frames, noise):
+@pytest.mark.parametrize("t,frames,noise,top_k", [(6, 1, 2e-3, 50), (3, 2, 1e-3, 50), (7, 3, 5e-4, 50), (1, 1, 1e-3, 50),
+                                                  (3, 1, 1e-3, 100)])
+def test_near_constant_keys_take_the_exact_tiled_pass(t, frames, noise, top_k):
     """Keys that differ by less than the filter's bf16 error margin (what networks with random weights produce for
     every frame of a video): every list overflows, the finalizer hands the queries to overflow_exact_kernel, which
     scores them exactly in 32 x 128 tiles.  Same arithmetic as the SIMT path - identical indices - and the oracle's
-    top-k.  6 / 7 frames (>= 64 blocks of 128 positions): the threshold pass samples every 4th block; 3 frames: all."""
+    top-k.  3 - 7 frames (>= 16 blocks of 128 positions): the threshold pass samples every 4th block; 1 frame (13
+    blocks): every 2nd; top_k = 100 (> 64): all of them."""
     import evavos_b200 as ev
     from evavos_b200 import _lib
     from evavos_b200.memory_reader import last_overflow_count
@@ -258,9 +260,9 @@ def test_near_constant_keys_take_the_exact_tiled_pass(t, frames, noise):
     qk = base.view(1, 64, *([1] * (len(shape) - 2))) * 0.9 + noise * torch.randn(shape, generator=g)
     mv = torch.randn(2, 32, t, h, w, generator=g)
     bank = ev.MemoryBank.from_tensors(mk.to(dev), mv.to(dev))
-    out_t, aff_t = ev.memory_read(bank, qk.to(dev), 50, want_topk=True, path=_lib.PATH_TENSOR_DENSE)
+    out_t, aff_t = ev.memory_read(bank, qk.to(dev), top_k, want_topk=True, path=_lib.PATH_TENSOR_DENSE)
     n_over = last_overflow_count()
-    out_x, aff_x = ev.memory_read(bank, qk.to(dev), 50, want_topk=True, path=_lib.PATH_SIMT)
+    out_x, aff_x = ev.memory_read(bank, qk.to(dev), top_k, want_topk=True, path=_lib.PATH_SIMT)
     assert last_overflow_count() == 0
     nq = frames * h * w
     assert n_over > 0.9 * nq, f"only {n_over} of {nq} queries overflowed: the test does not reach the tiled pass"
@@ -270,11 +272,11 @@ def test_near_constant_keys_take_the_exact_tiled_pass(t, frames, noise):
     # PATH_TENSOR launches the tiled pass only after a read has reported an overflow (the hint of api.cu); before
     # that a warp of the finalizer redoes each overflowed query - the result is the same either way
     for _ in range(2):
-        out_h, aff_h = ev.memory_read(bank, qk.to(dev), 50, want_topk=True, path=_lib.PATH_TENSOR)
+        out_h, aff_h = ev.memory_read(bank, qk.to(dev), top_k, want_topk=True, path=_lib.PATH_TENSOR)
         assert last_overflow_count() == n_over
         assert torch.equal(aff_h.idx, aff_x.idx) and torch.equal(out_h, out_x)
     s64 = onp.affinity_scores(mk[0].reshape(64, -1).numpy(), qk[0].reshape(64, -1).numpy())
-    exact, tie, bad, bad_q = onp.compare_topk(aff_t.idx.cpu().numpy(), s64, 50, TIE_TOL)
+    exact, tie, bad, bad_q = onp.compare_topk(aff_t.idx.cpu().numpy(), s64, top_k, TIE_TOL)
     assert bad == 0, bad_q[:5]
 
 
