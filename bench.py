@@ -343,12 +343,15 @@ def side_workload(name, args, dev, stream, pk, want_baseline=True):
 
 
 # ----------------------------------------------------------------------------------------------- sharded cfg4
-def run_sharded(args, cfg, rank, world, local_rank, dist=None, emit=True):
+def run_sharded(args, cfg, rank, world, local_rank, dist=None, emit=True, memory_shards=None):
     """cfg4: one long bank sharded by frame over the ranks; strong scaling (total work fixed).
 
+    memory_shards = M < world: the ranks form world / M query groups, each holding the whole bank sharded over its M
+    ranks and answering its own slice of the queries (evavos_b200.sharded.HybridShardedBank); M = world (default) is
+    the plain memory-axis sharded read.
     Returns the result dict (rank 0) - printed as its own line only with --workload cfg4."""
     import evavos_b200 as ev
-    from evavos_b200.sharded import ShardedMemoryBank
+    from evavos_b200.sharded import HybridShardedBank
     ck, cv, t, h, w, k, seed, desc = cfg
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -361,10 +364,11 @@ def run_sharded(args, cfg, rank, world, local_rank, dist=None, emit=True):
     hw, n_pos = h * w, t * h * w
     n_banks = 2
     steps = max(5, min(args.steps, 50))
+    m_shards = world if memory_shards is None else int(memory_shards)
     banks, full, queries = [], [], []
     for b in range(n_banks):
         g = torch.Generator(device=dev).manual_seed(seed + 100 * b)      # the same stream of frames on every rank
-        bank = ShardedMemoryBank(k, ck, cv, h, w, t, dev)
+        bank = HybridShardedBank(k, ck, cv, h, w, t, dev, m_shards)
         whole = ev.MemoryBank(k, ck, cv, h, w, t, dev, keep_reference_layout=False) if b == 0 else None
         for f in range(t):
             kf = torch.randn(1, ck, h, w, generator=g, device=dev)
@@ -380,20 +384,20 @@ def run_sharded(args, cfg, rank, world, local_rank, dist=None, emit=True):
     def step(i):
         # mem_freq = 5 query frames share one bank state (inference_core.py:174): one exchange for all of them;
         # every rank ends with the readout of the query slice it owns (the decoder consumes it where it is)
-        return banks[i % n_banks].read(queries[i % n_banks], TOP_K, scatter=True)
+        return banks[i % n_banks].read(queries[i % n_banks], TOP_K)
 
     def step_single(i):
         return ev.memory_read(full[0], queries[i % n_banks], TOP_K)[0]
 
     # parity: every rank's sharded result against its own single-bank read of the same bank
-    from evavos_b200.sharded import query_slice
-    out_s, idx_s, w_s = banks[0].read(queries[0], TOP_K, return_topk=True, scatter=True)
+    out_s, idx_s, w_s = banks[0].read(queries[0], TOP_K, return_topk=True)
     out_1, aff_1 = ev.memory_read(full[0], queries[0], TOP_K, want_topk=True)
     torch.cuda.synchronize(dev)
-    q0, q1 = query_slice(MEM_FREQ * hw, rank, world)
+    qa, qb = banks[0].query_range(MEM_FREQ * hw)        # the queries this rank's group answers
+    q0, q1 = banks[0].owned_slice(MEM_FREQ * hw)        # ... and the ones whose readout this rank ends up with
     ref_slice = out_1.reshape(k, cv, MEM_FREQ * hw)[:, :, q0:q1]
     rel = float(((out_s - ref_slice).norm() / ref_slice.norm()).item())
-    same_idx = bool(torch.equal(idx_s, aff_1.idx))
+    same_idx = bool(torch.equal(idx_s, aff_1.idx[qa:qb]))
     parity = torch.tensor([1.0 if (rel < 1e-5 and same_idx) else 0.0, rel], device=dev, dtype=torch.float64)
 
     for i in range(max(3, args.warmup)):
@@ -436,9 +440,13 @@ def run_sharded(args, cfg, rank, world, local_rank, dist=None, emit=True):
         res = {
             "metric": "memory-read query-frames/sec", "value": value, "unit": "query-frames/s", "n_gpus": world,
             "steps": steps, "ms_per_step": elapsed_ms / steps, "scaling": "strong", "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg4: " + desc + f", memory axis sharded by frame over {world} GPU(s)", "top_k": TOP_K,
+            "config": {"workload": "cfg4: " + desc + (f", memory axis sharded by frame over {world} GPU(s)" if m_shards == world else
+                                                      f", {world // m_shards} query groups x {m_shards} memory shards"), "top_k": TOP_K,
                        "memory_positions": n_pos, "queries_per_frame": hw, "objects": k, "query_frames_per_step": MEM_FREQ,
-                       "parallelism": f"memory-axis shards x{world}", "exchange": getattr(banks[0], "exchange_desc", "all-gather(top-k) + all-reduce(readout)")},
+                       "parallelism": f"memory-axis shards x{world}" if m_shards == world else
+                                      f"query groups x{world // m_shards}, memory-axis shards x{m_shards}",
+                       "memory_shards": m_shards, "bank_fraction_per_gpu": 1.0 / m_shards,
+                       "exchange": getattr(banks[0], "exchange_desc", "all-gather(top-k) + all-reduce(readout)")},
             "single_gpu_same_run": {"value": single, "ms_per_step": single_ms / steps,
                                     "note": "the same 5-frame read against the whole bank on ONE GPU, timed in this run"},
             "efficiency_vs_same_run_single_gpu": value / (world * single),
@@ -731,6 +739,18 @@ def run_ours(args, cfg, rank, world, local_rank):
     sharded = None
     if world > 1:
         sharded = run_sharded(args, WORKLOADS["cfg4"], rank, world, local_rank, dist=dist, emit=False)
+        # the same read with the queries split as well: world / M query groups x M memory shards (1 / M of the bank per GPU)
+        hybrid = {}
+        for m in (world // 2, world // 4, 1):
+            if m >= 1 and world % m == 0 and f"x{m}" not in hybrid:
+                r = run_sharded(args, WORKLOADS["cfg4"], rank, world, local_rank, dist=dist, emit=False, memory_shards=m)
+                if r is not None:
+                    hybrid[f"x{m}"] = {key: r[key] for key in ("value", "ms_per_step", "efficiency_vs_same_run_single_gpu",
+                                                              "speedup_vs_same_run_single_gpu", "per_rank_stage_us_max",
+                                                              "parity_ok", "parity_rel_l2_max")}
+                    hybrid[f"x{m}"].update(parallelism=r["config"]["parallelism"], bank_fraction_per_gpu=1.0 / m)
+                else:
+                    hybrid[f"x{m}"] = None
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -797,6 +817,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                 line[name] = {"error": repr(e)[:300]}
     if sharded is not None:
         line["sharded_cfg4"] = sharded
+        line["hybrid_cfg4"] = {k_: v_ for k_, v_ in hybrid.items() if v_ is not None}
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()

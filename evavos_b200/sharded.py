@@ -421,6 +421,86 @@ class ShardedMemoryBank:
         return {k: v / max(n, 1) for k, v in acc.items()}
 
 
+_SUBGROUPS: dict = {}     # (parent group, memory_shards) -> the sub-groups of HybridShardedBank
+
+
+class HybridShardedBank:
+    """world = query_groups x memory_shards: the bank is sharded along the memory axis over the ``memory_shards`` ranks
+    of a group (a ShardedMemoryBank on a sub-group) and replicated across the groups; every group answers its own
+    contiguous slice of the queries.
+
+    Why: what a rank pays per QUERY in the sharded read - thresholds, candidate lists, the finalizer, the merge, the
+    barriers - does not shrink with the memory shard, so G-way memory sharding of a fixed read
+    stops scaling early.  Splitting the queries as well divides exactly those costs, at the price of 1/memory_shards
+    instead of 1/world of the bank per GPU.  ``memory_shards = world`` is the plain memory-axis sharded read,
+    ``memory_shards = 1`` pure query parallelism over replicated banks (no exchange at all).
+
+    ``read`` returns (K, CV, q1 - q0): the readout of queries [q0, q1) = ``owned_slice(nq)`` of the flattened query
+    axis, in the reference layout - the scattered form the decoder consumes where it is.
+    """
+
+    def __init__(self, num_objects, key_dim, value_dim, height, width, capacity_frames, device, memory_shards,
+                 group=None, **kw):
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        m = int(memory_shards)
+        if m < 1 or world % m != 0:
+            raise ValueError(f"memory_shards={memory_shards} must divide the world size {world}")
+        self.world, self.rank, self.memory_shards, self.query_groups = world, rank, m, world // m
+        self.qgroup, self.mshard = rank // m, rank % m
+        self.CK = key_dim
+        sub = None
+        if world > 1:
+            key = (id(group) if group is not None else 0, m)
+            subs = _SUBGROUPS.get(key)
+            if subs is None:                         # created once per (parent group, M) and shared by all banks
+                parent = dist.get_process_group_ranks(group) if group is not None else list(range(world))
+                # new_group is collective: every rank creates every sub-group, in the same order
+                subs = _SUBGROUPS[key] = [dist.new_group([parent[g * m + j] for j in range(m)])
+                                          for g in range(self.query_groups)]
+            sub = subs[self.qgroup]
+        self.subgroup = sub
+        self.bank = ShardedMemoryBank(num_objects, key_dim, value_dim, height, width, capacity_frames, device,
+                                      group=sub, **kw)
+
+    def append(self, key_frame, value_frame) -> int:
+        """Called on every rank with the same frame: every group stores it, on its rank frame % memory_shards."""
+        return self.bank.append(key_frame, value_frame)
+
+    @property
+    def n_pos(self) -> int:
+        return self.bank.n_pos
+
+    @property
+    def exchange_desc(self) -> str:
+        return self.bank.exchange_desc if self.memory_shards > 1 else "none (replicated banks, queries split)"
+
+    def query_range(self, nq: int):
+        """Queries [a, b) this rank's group answers."""
+        return query_slice(nq, self.qgroup, self.query_groups)
+
+    def owned_slice(self, nq: int):
+        """Queries [q0, q1) whose readout this rank ends up with."""
+        a, b = self.query_range(nq)
+        q0, q1 = query_slice(b - a, self.mshard, self.memory_shards)
+        return a + q0, a + q1
+
+    def read(self, qk: torch.Tensor, top_k: int = 50, return_topk: bool = False, timing: dict | None = None):
+        flat = qk.reshape(1, qk.shape[1], -1)
+        a, b = self.query_range(flat.shape[2])
+        return self.bank.read(flat[:, :, a:b], top_k, return_topk=return_topk, scatter=True, timing=timing)
+
+    def profile(self, qk, top_k=50, reps=10):
+        flat = qk.reshape(1, qk.shape[1], -1)
+        a, b = self.query_range(flat.shape[2])
+        if self.memory_shards == 1:
+            return {}
+        return self.bank.profile(flat[:, :, a:b], top_k, reps)
+
+    def close(self):
+        self.bank.close()
+
+
 def _accepts_out(ops) -> bool:
     import inspect
     try:

@@ -133,3 +133,58 @@ def test_peer_memory_exchange_two_ranks_on_one_gpu():
 def test_sharded_read_over_nvlink_two_gpus():
     """Both exchange engines (peer memory, NCCL) with one GPU per rank."""
     _run_ranks(2, "nccl", False)
+
+
+def _hybrid_worker(rank, world, port, ret, memory_shards):
+    """Four (or two) processes on cuda:0: world / M query groups x M memory shards, peer-memory exchange inside each
+    group (gloo only carries the IPC handles)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from evavos_b200.sharded import HybridShardedBank
+        K, CK, CV, T, H, W = 2, 64, 512, 9, 12, 16
+        mk, _, mv = synth(27, CK, CV, T, H, W, K)
+        qk = torch.randn(1, CK, 3, H, W, generator=torch.Generator().manual_seed(28))
+        nq = 3 * H * W
+        tk, ro = onp.memory_read(mk[0].reshape(CK, -1).numpy(), qk[0].reshape(CK, -1).numpy(), mv.reshape(K, CV, -1).numpy(), 50)
+        bank = HybridShardedBank(K, CK, CV, H, W, T, dev, memory_shards)
+        for f in range(T):
+            bank.append(mk[:, :, f].to(dev), mv[:, :, f:f + 1].to(dev))
+        a, b = bank.query_range(nq)
+        q0, q1 = bank.owned_slice(nq)
+        for rep in range(2):
+            mine, gidx, w = bank.read(qk.to(dev), 50, return_topk=True)
+            torch.cuda.synchronize()
+            assert mine.shape == (K, CV, q1 - q0)
+            assert (gidx.cpu().numpy() == tk.idx[a:b]).all()
+            assert np.abs(w.cpu().numpy() - tk.weight[a:b]).max() < 1e-6
+            assert onp.rel_l2(mine.cpu().numpy(), ro[:, :, q0:q1]) < 1e-5
+            plain = bank.read(qk.to(dev), 50)
+            assert torch.equal(plain, mine)
+        bank.close()
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,memory_shards", [(4, 2), (2, 1)])
+def test_hybrid_query_groups_and_memory_shards_on_one_gpu(world, memory_shards):
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_hybrid_worker, args=(r, world, port, ret, memory_shards)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        if p.is_alive():
+            p.terminate()
+        assert p.exitcode == 0
+    assert all(ret.get(r) for r in range(world))

@@ -120,3 +120,58 @@ def test_sharded_read_matches_single_bank(world, frames, top_k):
         p.join(180)
         assert p.exitcode == 0
     assert all(ret.get(r) for r in range(world))
+
+
+def _hybrid_worker(rank, world, port, memory_shards, frames, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from evavos_b200.sharded import HybridShardedBank
+        K, CK, CV, H, W, top_k = 2, 64, 12, 5, 6, 20
+        g = torch.Generator().manual_seed(7)
+        mk = torch.randn(1, CK, frames, H, W, generator=g)
+        mv = torch.randn(K, CV, frames, H, W, generator=g)
+        qk = torch.randn(1, CK, 3, H, W, generator=g)
+        bank = HybridShardedBank(K, CK, CV, H, W, frames, "cpu", memory_shards, bank_factory=_CpuBank, ops=_OracleOps())
+        assert (bank.query_groups, bank.qgroup, bank.mshard) == (world // memory_shards, rank // memory_shards,
+                                                                 rank % memory_shards)
+        for f in range(frames):
+            bank.append(mk[:, :, f], mv[:, :, f:f + 1])
+        # every group holds the whole bank, split over its memory shards
+        assert bank.bank.local.n_frames == len(range(bank.mshard, frames, memory_shards))
+        nq = 3 * H * W
+        out, gidx, w = bank.read(qk, top_k, return_topk=True)
+        tk, ro = onp.memory_read(mk[0].reshape(CK, -1).numpy(), qk[0].reshape(CK, -1).numpy(),
+                                 mv.reshape(K, CV, -1).numpy(), top_k)
+        a, b = bank.query_range(nq)
+        q0, q1 = bank.owned_slice(nq)
+        assert a <= q0 <= q1 <= b and out.shape == (K, CV, q1 - q0)
+        assert (gidx.numpy() == tk.idx[a:b]).all()
+        assert np.abs(out.numpy() - ro[:, :, q0:q1]).max() < 1e-5
+        # the owned slices of all ranks tile the query axis exactly once
+        spans = [None] * world
+        dist.all_gather_object(spans, (q0, q1))
+        covered = sorted(spans)
+        assert covered[0][0] == 0 and covered[-1][1] == nq and all(x[1] == y[0] for x, y in zip(covered, covered[1:]))
+        bank.close()
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,memory_shards,frames", [(2, 1, 5), (2, 2, 5), (4, 2, 6)])
+def test_hybrid_query_groups_times_memory_shards(world, memory_shards, frames):
+    """world = query groups x memory shards (HybridShardedBank): every group answers its slice of the queries against
+    a bank sharded over its own ranks; together the ranks hold every query's readout exactly once."""
+    ctx = mp.get_context("spawn")
+    mgr = ctx.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_hybrid_worker, args=(r, world, port, memory_shards, frames, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+        assert p.exitcode == 0
+    assert all(ret.get(r) for r in range(world))
