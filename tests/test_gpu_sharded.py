@@ -163,8 +163,8 @@ def _hybrid_worker(rank, world, port, ret, memory_shards):
             assert (gidx.cpu().numpy() == tk.idx[a:b]).all()
             assert np.abs(w.cpu().numpy() - tk.weight[a:b]).max() < 1e-6
             assert onp.rel_l2(mine.cpu().numpy(), ro[:, :, q0:q1]) < 1e-5
-            plain = bank.read(qk.to(dev), 50)
-            assert torch.equal(plain, mine)
+            plain = bank.read(qk.to(dev), 50)     # (M = 1: the ordinary fused read; M > 1: the same exchange again)
+            assert onp.rel_l2(plain.cpu().numpy(), ro[:, :, q0:q1]) < 1e-5
         bank.close()
         ret[rank] = True
     finally:
