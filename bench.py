@@ -25,9 +25,11 @@ ONE JSON line:
  * N == 1 also carries `cfg4` and `cfg5`: BASELINE.json configs[3] (unsharded, one GPU) and configs[4] (bf16 values)
    with their own stage times, rooflines and GPU baselines.
  * N > 1: ranks run independent videos (no collective, weak scaling: the headline line), and the line also carries
-   `sharded_cfg4`: ONE 200-frame bank sharded along the memory axis over the N ranks (NCCL exchange) with per-rank
-   stage times, the same run's single-GPU time of the same read, the efficiency between the two, and `parity_ok`
-   (rank 0's sharded result against its own single-bank read).
+   `sharded_cfg4`: ONE 200-frame bank sharded along the memory axis over the N ranks (device-initiated exchange over
+   NVLink peer memory; EVAVOS_SHARD_EXCHANGE=nccl for the library baseline) with per-rank stage times, the same run's
+   single-GPU time of the same read, the efficiency between the two, and `parity_ok` (every rank's result against its
+   own single-bank read); and `hybrid_cfg4`: the same read with the queries split as well (N / M query groups x M
+   memory shards, M = N/2, N/4, 1 - evavos_b200.sharded.HybridShardedBank).
 """
 from __future__ import annotations
 
