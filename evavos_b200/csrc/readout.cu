@@ -11,7 +11,11 @@ namespace evavos {
 
 namespace {
 
-constexpr int kQPerCta = 8;  // one warp per query
+#ifndef EVAVOS_READOUT_Q
+#define EVAVOS_READOUT_Q 8
+#endif
+constexpr int kQPerCta = EVAVOS_READOUT_Q;  // one warp per query
+constexpr int kRoThreads = 32 * kQPerCta;
 
 // Value rows of one query in flight per lane group.  Measured on B200 (cfg2, cold L2): 2, 5 and 10 give the same
 // 37 us, and ld.global.nc.L1::no_allocate is slower (45 us): the kernel sits on the L2/HBM path, not on latency.
@@ -38,7 +42,7 @@ __device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
 // QMAJOR: the output is (n_query, K, CV) - one contiguous K*CV row per query, written straight from the registers
 // (the layout the sharded read reduces over: a query slice is a contiguous chunk); out_*_stride are ignored.
 template <int NV, bool QMAJOR>
-__global__ void __launch_bounds__(256) readout_f32_kernel(
+__global__ void __launch_bounds__(kRoThreads) readout_f32_kernel(
     const float* __restrict__ val_pm_all, int64_t capacity_pos, int CVfull, const int32_t* __restrict__ idx,
     const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out_all,
     int64_t out_obj_stride, int64_t out_ch_stride, int q_per_frame, int64_t frame_stride) {
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(256) readout_f32_kernel(
   }
   __syncthreads();
   const int nq_here = (int)min((int64_t)kQPerCta, n_query - q0);
-  for (int e = threadIdx.x; e < CV * kQPerCta; e += 256) {
+  for (int e = threadIdx.x; e < CV * kQPerCta; e += kRoThreads) {
     const int c = e / kQPerCta, w = e % kQPerCta;
     if (w < nq_here)
       out[(int64_t)o * out_obj_stride + (int64_t)c * out_ch_stride + query_offset(q0 + w, q_per_frame, frame_stride)] = st[c][w];
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(256) readout_f32_kernel(
 
 // bf16 rows, CV = 256 * NV (8 bf16 per 16-byte load), fp32 accumulation.
 template <int NV, bool QMAJOR>
-__global__ void __launch_bounds__(256) readout_bf16_kernel(
+__global__ void __launch_bounds__(kRoThreads) readout_bf16_kernel(
     const __nv_bfloat16* __restrict__ val_pm, int64_t capacity_pos, const int32_t* __restrict__ idx,
     const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out,
     int64_t out_obj_stride, int64_t out_ch_stride, int q_per_frame, int64_t frame_stride) {
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(256) readout_bf16_kernel(
     for (int e = 0; e < 8; ++e) st[i * 256 + lane * 8 + e][warp] = acc[i][e];
   __syncthreads();
   const int nq_here = (int)min((int64_t)kQPerCta, n_query - q0);
-  for (int e = threadIdx.x; e < CV * kQPerCta; e += 256) {
+  for (int e = threadIdx.x; e < CV * kQPerCta; e += kRoThreads) {
     const int c = e / kQPerCta, w = e % kQPerCta;
     if (w < nq_here)
       out[(int64_t)o * out_obj_stride + (int64_t)c * out_ch_stride + query_offset(q0 + w, q_per_frame, frame_stride)] = st[c][w];
@@ -222,12 +226,12 @@ int launch_readout(const EvavosBankShadow& b, const int32_t* idx, const float* w
   const dim3 grid((unsigned)ceil_div(n_query, kQPerCta), (unsigned)b.K);
   const bool row16 = (reinterpret_cast<uintptr_t>(b.val_pm) % 16) == 0;
 #define EVAVOS_RO_F32_(NV, SPLIT, QM)                                                                         \
-  EVAVOS_CUDA_OK(launch_pdl(readout_f32_kernel<NV, QM>, dim3(grid.x, grid.y, SPLIT), dim3(256), 0, st,        \
+  EVAVOS_CUDA_OK(launch_pdl(readout_f32_kernel<NV, QM>, dim3(grid.x, grid.y, SPLIT), dim3(kRoThreads), 0, st,        \
                             reinterpret_cast<const float*>(b.val_pm), b.capacity_pos, b.CV, idx, weight,      \
                             n_query, top_k, out, out_obj_stride, out_ch_stride, q_per_frame, frame_stride))
 #define EVAVOS_RO_F32(NV, SPLIT) do { if (qmajor) EVAVOS_RO_F32_(NV, SPLIT, true); else EVAVOS_RO_F32_(NV, SPLIT, false); } while (0)
 #define EVAVOS_RO_BF16_(NV, QM)                                                                               \
-  EVAVOS_CUDA_OK(launch_pdl(readout_bf16_kernel<NV, QM>, grid, dim3(256), 0, st,                              \
+  EVAVOS_CUDA_OK(launch_pdl(readout_bf16_kernel<NV, QM>, grid, dim3(kRoThreads), 0, st,                              \
                             reinterpret_cast<const __nv_bfloat16*>(b.val_pm), b.capacity_pos, idx, weight,    \
                             n_query, top_k, out, out_obj_stride, out_ch_stride, q_per_frame, frame_stride))
 #define EVAVOS_RO_BF16(NV) do { if (qmajor) EVAVOS_RO_BF16_(NV, true); else EVAVOS_RO_BF16_(NV, false); } while (0)

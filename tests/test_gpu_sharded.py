@@ -61,7 +61,7 @@ def test_two_shards_on_one_device_equal_single_bank():
     assert onp.rel_l2(total.cpu().numpy().reshape(ro.shape), ro) < 1e-5
 
 
-def _sharded_worker(rank, world, port, ret, backend, same_device):
+def _sharded_worker(rank, world, port, ret, backend, same_device, degenerate=False):
     """One rank of a sharded read.  backend "nccl": one GPU per rank, both exchange engines.  backend "gloo" with
     same_device: all ranks share cuda:0 (CUDA IPC works between processes on one device) - the peer-memory engine
     needs no NCCL at all, only a process group to pass the IPC handles, so it can be checked on a 1-GPU box."""
@@ -79,6 +79,17 @@ def _sharded_worker(rank, world, port, ret, backend, same_device):
         K, CK, CV, T, H, W = 2, 64, 512, 9, 12, 16
         mk, _, mv = synth(17, CK, CV, T, H, W, K)
         qk = torch.randn(1, CK, 3, H, W, generator=torch.Generator().manual_seed(18))     # 3 query frames, 576 queries
+        if degenerate:
+            # near-constant keys: every local candidate list overflows (> 1 024 of a shard's ~5 800 positions inside the
+            # filter's margin), so the lists the peers receive come from the finalizer's own exact path on the first
+            # read and from overflow_exact_kernel's finalizer afterwards (the overflow hint of api.cu)
+            T, H, W = 12, 30, 32
+            g = torch.Generator().manual_seed(19)
+            base = torch.randn(1, CK, 1, 1, 1, generator=g)
+            mk = base + 1e-3 * torch.randn(1, CK, T, H, W, generator=g)
+            mv = torch.randn(K, CV, T, H, W, generator=g)
+            qk = (0.9 * base + 1e-3 * torch.randn(1, CK, 1, H, W, generator=g))[:, :, :, :8].contiguous()      # 256 queries
+        n_queries = qk.shape[2] * qk.shape[3] * qk.shape[4]
         tk, ro = onp.memory_read(mk[0].reshape(CK, -1).numpy(), qk[0].reshape(CK, -1).numpy(), mv.reshape(K, CV, -1).numpy(), 50)
         engines = ["peer", "nccl"] if backend == "nccl" else ["peer"]
         for engine in engines:
@@ -88,8 +99,16 @@ def _sharded_worker(rank, world, port, ret, backend, same_device):
             for rep in range(3):      # several reads through the same exchange buffers (barrier epochs, buffer reuse)
                 mine, gidx, w = bank.read(qk.to(dev), 50, return_topk=True, scatter=True)
                 torch.cuda.synchronize()
-                q0, q1 = query_slice(3 * H * W, rank, world)
+                q0, q1 = query_slice(n_queries, rank, world)
                 assert mine.shape == (K, CV, q1 - q0)
+                if degenerate:       # near-ties: compare the selection tie-aware, the readout against the oracle's
+                    s64 = onp.affinity_scores(mk[0].reshape(CK, -1).numpy(), qk[0].reshape(CK, -1).numpy())
+                    from tests.helpers import TIE_TOL
+                    assert onp.compare_topk(gidx.cpu().numpy(), s64, 50, TIE_TOL)[2] == 0
+                    own = onp.readout(gidx.cpu().numpy().astype(np.int64), w.cpu().numpy().astype(np.float64),
+                                      mv.reshape(K, CV, -1).numpy())
+                    assert onp.rel_l2(mine.cpu().numpy(), own[:, :, q0:q1]) < 1e-5
+                    continue
                 assert (gidx.cpu().numpy() == tk.idx).all(), engine
                 assert np.abs(w.cpu().numpy() - tk.weight).max() < 1e-6
                 err = onp.rel_l2(mine.cpu().numpy(), ro[:, :, q0:q1])
@@ -105,14 +124,15 @@ def _sharded_worker(rank, world, port, ret, backend, same_device):
         dist.destroy_process_group()
 
 
-def _run_ranks(world, backend, same_device):
+def _run_ranks(world, backend, same_device, degenerate=False):
     import torch.multiprocessing as mp
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
-    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, ret, backend, same_device)) for r in range(world)]
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, ret, backend, same_device, degenerate))
+             for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
@@ -127,6 +147,11 @@ def test_peer_memory_exchange_two_ranks_on_one_gpu():
     """The device-initiated exchange (finalizer push over IPC-mapped peer buffers, device-side barriers, reduce-scatter
     by peer loads) with two processes sharing cuda:0: no NCCL involved, so it runs on the driver's 1-GPU box."""
     _run_ranks(2, "gloo", True)
+
+
+def test_peer_memory_exchange_with_overflowed_lists():
+    """Near-constant keys: the pushed lists come from the exact paths (finalizer warp, then the tiled overflow pass)."""
+    _run_ranks(2, "gloo", True, degenerate=True)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
