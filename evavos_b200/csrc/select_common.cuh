@@ -89,11 +89,12 @@ struct FinalizeWarpSmem {
 
 // A lower bound (20 leading bits) of the k-th largest filter score among list[0..n): radix descent over the
 // order-preserving keys, NJ entries per lane in registers.  n <= 32 * NJ, k <= n.
+// low_bit = 0 resolves all 32 bits: the k-th largest key itself.
 template <int NJ>
-__device__ __forceinline__ uint32_t kth_largest_bound(const uint32_t* key, int k) {
+__device__ __forceinline__ uint32_t kth_largest_bound(const uint32_t* key, int k, int low_bit = 12) {
   uint32_t prefix = 0;
   int need = k;
-  for (int bit = 31; bit >= 12; --bit) {
+  for (int bit = 31; bit >= low_bit; --bit) {
     const uint32_t want = (prefix >> bit) | 1u;
     int c = 0;
 #pragma unroll
@@ -111,7 +112,10 @@ __device__ __forceinline__ uint32_t kth_largest_bound(const uint32_t* key, int k
 // >= theta - 2 eps.  Returns ns.  The survivors' positions are also compacted IN PLACE into list[0..ns).x (a slot
 // never lies beyond the entries already read), which is where a query with more than kMaxSurvivors of them - a big
 // cluster of near-ties, e.g. a static background seen in hundreds of memory frames - is finished from, in batches.
-template <int NJ>
+// EXACT: the listed scores are exact (overflow_exact_kernel; the arithmetic of rescore_rows): the cut is the k-th
+// largest score itself - with near-constant keys a 20-bit bound lies below EVERY listed score and nothing would be
+// cut - and the survivors' (score, position) keys are complete as they are: sm.keys receives them, nothing is rescored.
+template <int NJ, bool EXACT = false>
 __device__ __forceinline__ int prefilter_candidates(FinalizeWarpSmem& sm, int2* list, int n, int k, float two_eps,
                                                     int lane) {
   uint32_t key[NJ];
@@ -120,8 +124,13 @@ __device__ __forceinline__ int prefilter_candidates(FinalizeWarpSmem& sm, int2* 
     const int e = lane + 32 * j;
     key[j] = e < n ? float_to_ordered(__int_as_float(__ldcg(&list[e].y))) : 0u;
   }
-  const float theta = ordered_to_float(kth_largest_bound<NJ>(key, k));
-  const uint32_t cut = float_to_ordered(theta - two_eps);
+  uint32_t cut;
+  if constexpr (EXACT) {
+    cut = kth_largest_bound<NJ>(key, k, 0);
+  } else {
+    const float theta = ordered_to_float(kth_largest_bound<NJ>(key, k));
+    cut = float_to_ordered(theta - two_eps);
+  }
   int ns = 0;
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
@@ -131,7 +140,10 @@ __device__ __forceinline__ int prefilter_candidates(FinalizeWarpSmem& sm, int2* 
     if (pass) {
       const int slot = ns + __popc(m & ((1u << lane) - 1u));
       const int32_t pos = __ldcg(&list[e].x);
-      if (slot < kMaxSurvivors) sm.keys[slot] = (unsigned long long)(uint32_t)pos;
+      if (slot < kMaxSurvivors) {
+        if constexpr (EXACT) sm.keys[slot] = ((unsigned long long)key[j] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)pos);
+        else sm.keys[slot] = (unsigned long long)(uint32_t)pos;
+      }
       list[slot].x = pos;
     }
     ns += __popc(m);
@@ -260,6 +272,7 @@ __device__ __forceinline__ void finalize_query_warp(FinalizeWarpSmem& sm, int la
   const int2* list = cand + q * kCandCap;
 
   int ns = -1;   // survivors (positions in sm.keys when <= kMaxSurvivors, else in list[].x), or -1: the exact path
+  bool keys_ready = false;   // sm.keys already holds exact (score, position) keys: nothing to rescore
   if (cnt_raw <= kCandCap) {
     int2* wlist = const_cast<int2*>(list);   // the lists are workspace: the cut compacts them in place
     if (!scored) {
@@ -269,7 +282,12 @@ __device__ __forceinline__ void finalize_query_warp(FinalizeWarpSmem& sm, int la
       // scored == 2: the list carries EXACT scores (overflow_exact_kernel): the cut needs no error margin
       const float two_eps = scored == 2 ? 0.f : 2.0f * filter_eps(sqrtf(qq), __ldg(key_maxnorm));
       const int k = min(top_k, cnt_raw);
-      if (cnt_raw <= top_k + 32) {   // a list this short is not worth cutting: rescore all of it
+      if (scored == 2) {
+        if (cnt_raw <= 256) ns = prefilter_candidates<8, true>(sm, wlist, cnt_raw, k, 0.f, lane);
+        else if (cnt_raw <= 512) ns = prefilter_candidates<16, true>(sm, wlist, cnt_raw, k, 0.f, lane);
+        else ns = prefilter_candidates<32, true>(sm, wlist, cnt_raw, k, 0.f, lane);
+        keys_ready = ns <= kMaxSurvivors;
+      } else if (cnt_raw <= top_k + 32) {   // a list this short is not worth cutting: rescore all of it
         ns = cnt_raw;
         for (int e = lane; e < ns; e += 32) sm.keys[e] = (unsigned long long)(uint32_t)__ldcg(&list[e].x);
       } else if (cnt_raw <= 256) ns = prefilter_candidates<8>(sm, wlist, cnt_raw, k, two_eps, lane);
@@ -282,7 +300,7 @@ __device__ __forceinline__ void finalize_query_warp(FinalizeWarpSmem& sm, int la
   if (ns < 0) {
     take = exact_topk_warp(sm, key_pm, CK, n_pos, top_k, qq, inv_sqrt_ck, lane);
   } else if (ns <= kMaxSurvivors) {
-    rescore_rows(sm, ns, key_pm, CK, qq, inv_sqrt_ck, lane);
+    if (!keys_ready) rescore_rows(sm, ns, key_pm, CK, qq, inv_sqrt_ck, lane);
     take = min(top_k, ns);
     rank_into_sel(sm, ns, take, lane);
   } else {

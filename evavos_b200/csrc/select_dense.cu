@@ -21,7 +21,18 @@ namespace evavos {
 
 namespace {
 
-constexpr int kOvQ = 32;       // queries per CTA tile (4 per warp)
+// Queries per warp (each lane holds kOvQW x 4 accumulators) and resident CTAs per SM.  Measured on B200 (8 100 queries x
+// 8 100 positions, whole read incl. filter, scripts/dense_time.py): 4 x 2 CTAs 844 us | 8 x 1 CTA 871 | 4 x 1 947 |
+// 8 x 2 (spills) 1 367.  With 4 the tile loop moves 20 LSU cycles per 16 FMA cycles, with 8 it is FMA-bound on paper -
+// but then only 8 warps fit an SM, and the kernel is latency-bound either way (FMA pipe ~30 % busy under ncu).
+#ifndef EVAVOS_OVQW
+#define EVAVOS_OVQW 4
+#endif
+#ifndef EVAVOS_OVMINB
+#define EVAVOS_OVMINB 2
+#endif
+constexpr int kOvQW = EVAVOS_OVQW;   // queries per warp
+constexpr int kOvQ = 8 * kOvQW;   // queries per CTA tile
 constexpr int kOvP = 128;      // positions per step (4 per lane); also the number of classes
 constexpr int kOvThreads = 256;
 constexpr int kOvWarps = kOvThreads / 32;
@@ -60,7 +71,7 @@ __device__ __forceinline__ void load_block(OverflowTiles& t, int buf, const floa
   cp_async_commit();
 }
 
-__global__ void __launch_bounds__(kOvThreads, 2) overflow_exact_kernel(
+__global__ void __launch_bounds__(kOvThreads, EVAVOS_OVMINB) overflow_exact_kernel(
     const float* __restrict__ key_pm, const float* __restrict__ query, int64_t query_ch_stride, int64_t n_pos,
     int64_t n_query, int top_k, int2* __restrict__ cand, const int32_t* __restrict__ overflow_list,
     const unsigned int* __restrict__ overflow_cnt, const float* __restrict__ key_maxnorm,
@@ -93,21 +104,23 @@ __global__ void __launch_bounds__(kOvThreads, 2) overflow_exact_kernel(
     }
     __syncthreads();
     for (int e = tid; e < kOvQ * 64; e += kOvThreads) {
-      const int qi = e & (kOvQ - 1), c = e >> 5;
+      const int qi = e % kOvQ, c = e / kOvQ;
       const int32_t qid = s_qid[qi];
       sm.t.q[qi][c] = qid >= 0 ? __ldg(query + (int64_t)c * query_ch_stride + qid) : 0.f;
     }
     __syncthreads();
-    float qq[4];
+    float qq[kOvQW];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) qq[j] = sumsq64_warp(sm.t.q[warp * 4 + j], lane);
+    for (int j = 0; j < kOvQW; ++j) qq[j] = sumsq64_warp(sm.t.q[warp * kOvQW + j], lane);
 
-    float cmax[4][4];
+    float cmax[kOvQW][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < kOvQW; ++j)
 #pragma unroll
       for (int i = 0; i < 4; ++i) cmax[j][i] = -INFINITY;
-    uint32_t bound[4] = {0u, 0u, 0u, 0u};   // order-preserving keys; pass 2 lists every score whose key reaches them
+    uint32_t bound[kOvQW];   // order-preserving keys; pass 2 lists every score whose key reaches them
+#pragma unroll
+    for (int j = 0; j < kOvQW; ++j) bound[j] = 0u;
 
     for (int pass = 1; pass <= 2; ++pass) {
       const int64_t step_blocks = pass == 1 ? sample : 1;
@@ -138,27 +151,27 @@ __global__ void __launch_bounds__(kOvThreads, 2) overflow_exact_kernel(
         }
         __syncthreads();
 
-        float acc[4][4];   // [query j][position i]: k.q, channels in order, one accumulator per pair
+        float acc[kOvQW][4];   // [query j][position i]: k.q, channels in order, one accumulator per pair
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < kOvQW; ++j)
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-#pragma unroll 4
+#pragma unroll 2
         for (int c4 = 0; c4 < 16; ++c4) {
-          float4 kv[4], qv[4];
+          float4 kv[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) kv[i] = *reinterpret_cast<const float4*>(&sm.t.k[buf][lane + 32 * i][4 * c4]);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) qv[j] = *reinterpret_cast<const float4*>(&sm.t.q[warp * 4 + j][4 * c4]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
+          for (int j = 0; j < kOvQW; ++j) {
+            const float4 qv = *reinterpret_cast<const float4*>(&sm.t.q[warp * kOvQW + j][4 * c4]);   // broadcast
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              acc[j][i] = fmaf(kv[i].x, qv[j].x, acc[j][i]);
-              acc[j][i] = fmaf(kv[i].y, qv[j].y, acc[j][i]);
-              acc[j][i] = fmaf(kv[i].z, qv[j].z, acc[j][i]);
-              acc[j][i] = fmaf(kv[i].w, qv[j].w, acc[j][i]);
+              acc[j][i] = fmaf(kv[i].x, qv.x, acc[j][i]);
+              acc[j][i] = fmaf(kv[i].y, qv.y, acc[j][i]);
+              acc[j][i] = fmaf(kv[i].z, qv.z, acc[j][i]);
+              acc[j][i] = fmaf(kv[i].w, qv.w, acc[j][i]);
             }
+          }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -166,12 +179,12 @@ __global__ void __launch_bounds__(kOvThreads, 2) overflow_exact_kernel(
           const bool live = n < n_pos;
           const float kk = sm.t.kk[buf][lane + 32 * i];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < kOvQW; ++j) {
             const float sc = affinity_from_parts(kk, acc[j][i], qq[j], inv_sqrt_ck);
             if (pass == 1) {
               if (live) cmax[j][i] = fmaxf(cmax[j][i], sc);
             } else if (live && float_to_ordered(sc) >= bound[j]) {
-              const int qi = warp * 4 + j;
+              const int qi = warp * kOvQW + j;
               const int32_t qid = s_qid[qi];
               if (qid >= 0) {
                 const int slot = atomicAdd(&s_cnt[qi], 1);
@@ -185,7 +198,7 @@ __global__ void __launch_bounds__(kOvThreads, 2) overflow_exact_kernel(
       if (pass == 1) {
         const int k = top_k < kOvP ? top_k : kOvP;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kOvQW; ++j) {
           uint32_t key[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) key[i] = float_to_ordered(cmax[j][i]);
@@ -196,8 +209,8 @@ __global__ void __launch_bounds__(kOvThreads, 2) overflow_exact_kernel(
 
     // pass 3: the finalizer, one warp per query, on lists that carry exact scores (cut with a zero margin)
     __syncthreads();   // every listed entry is written; the tiles are dead
-    for (int j = 0; j < 4; ++j) {
-      const int qi = warp * 4 + j;
+    for (int j = 0; j < kOvQW; ++j) {
+      const int qi = warp * kOvQW + j;
       const int32_t qid = s_qid[qi];
       if (qid < 0) continue;
       finalize_query_warp(sm.fin[warp], lane, qid, key_pm, query, query_ch_stride, 64, n_pos, top_k, cand, s_cnt[qi],

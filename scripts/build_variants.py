@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from evavos_b200.build import CSRC, NVCC_FLAGS, SOURCES, _nvcc  # noqa: E402
 
-VARIANT_SOURCES = {"score_tc.cu", "select_simt.cu", "api.cu", "readout.cu"}
+VARIANT_SOURCES = {"score_tc.cu", "select_simt.cu", "api.cu", "readout.cu", "select_dense.cu"}
 OBJ = os.path.join(ROOT, "build", "obj")
 os.makedirs(OBJ, exist_ok=True)
 flags = [f for f in NVCC_FLAGS if f != "-shared"]
