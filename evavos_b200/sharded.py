@@ -451,7 +451,8 @@ class HybridShardedBank:
         self.CK = key_dim
         sub = None
         if world > 1:
-            key = (id(group) if group is not None else 0, m)
+            # (keyed on the live default group as well: sub-groups die with the process group that made them)
+            key = (id(dist.distributed_c10d._get_default_group()), id(group) if group is not None else 0, m)
             subs = _SUBGROUPS.get(key)
             if subs is None:                         # created once per (parent group, M) and shared by all banks
                 parent = dist.get_process_group_ranks(group) if group is not None else list(range(world))
