@@ -30,5 +30,22 @@ gi, w, loc = ops.merge_gathered(packed, 50, 0, 1, H * W)
 part = ops.readout(bank, loc, w)
 att = ev.attention_readout(mk[:, :, 1:2], qk, torch.rand(6, H * W, generator=g).to(dev))      # fusion-path attention read
 masks, unp = ev.argmax_unpad(torch.rand(3, 4, 1, 32, 48, device=dev), (3, 5, 2, 6), 24, 40)
+# round 2: multi-frame query batch into a frame-major destination, the overflow pass (near-constant keys, bank length not
+# a multiple of 128), query-major readout, J&F scoring, the peer barrier / reduce-scatter on a single rank
+qk3 = torch.randn(1, CK, 3, H, W, generator=g).to(dev)
+m4 = torch.empty((3, K, 2 * CV, H, W), device=dev)
+ev.memory_read(bank, qk3, 50, out=m4)
+base = torch.randn(1, CK, 1, 1, 1, generator=g)
+Td, Hd, Wd = 2, 24, 30                                                                  # 1 440 positions
+dense_bank = ev.MemoryBank.from_tensors((base + 1e-3 * torch.randn(1, CK, Td, Hd, Wd, generator=g)).to(dev),
+                                        torch.randn(1, 64, Td, Hd, Wd, generator=g).to(dev))
+qd = (0.9 * base[:, :, 0] + 1e-3 * torch.randn(1, CK, 5, 7, generator=g)).to(dev)
+for p_ in (_lib.PATH_TENSOR_DENSE, _lib.PATH_TENSOR):
+    out_d, aff_d = ev.memory_read(dense_bank, qd, 50, want_topk=True, path=p_)
+from evavos_b200.memory_reader import last_overflow_count
+n_over = last_overflow_count()
+pred = torch.rand(3, 37, 53, generator=g).to(dev) > 0.5
+gt = torch.rand(3, 37, 53, generator=g).to(dev) > 0.5
+jf = ev.frame_metrics(pred, gt)
 torch.cuda.synchronize()
-print("sanitize run ok", float(out.abs().mean()), float(part.abs().mean()))
+print("sanitize run ok", float(out.abs().mean()), float(part.abs().mean()), "overflowed queries:", n_over)
