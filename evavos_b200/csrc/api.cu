@@ -71,6 +71,8 @@ Carve carve_workspace(const EvavosMemReadArgs& a, int n_chunks, int n_sm, uint8_
     off += align_up(bytes, 1024);
     return p;
   };
+  // (per launch [chunks][query rows of the launch][128]; multi-wave reads - more query tiles than SMs - use at most
+  //  n_sm tile rows per launch, fewer than the nq_pad rows reserved here)
   c.sb.class_max = reinterpret_cast<float*>(take(n_chunks > 0 ? sizeof(float) * (size_t)n_chunks * nq_pad * 128 : 0));
   c.sb.tau = reinterpret_cast<float*>(take(sizeof(float) * nq_pad));
   c.sb.cand_cnt = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * nq_pad));

@@ -254,6 +254,8 @@ struct PassParams {
   int64_t n_pos;
   int64_t n_query;
   int64_t nq_pad;
+  int64_t cm_row0;      // class_max holds the rows of THIS launch only: row (q - cm_row0) of cm_rows, per chunk
+  int64_t cm_rows;
   int n_mtiles;
   int n_ktiles;
   int n_chunks;
@@ -369,8 +371,8 @@ __device__ __forceinline__ void warp_threshold(const PassParams& p, int64_t q, i
   float v[4] = {kEmptyNh, kEmptyNh, kEmptyNh, kEmptyNh};
   {
     // 8 chunks x 4 classes = 32 independent L2 loads per round (the rows were written by other CTAs: bypass L1)
-    const float* row0 = p.class_max + q * 128 + lane;
-    const int64_t chunk_stride = p.nq_pad * 128;
+    const float* row0 = p.class_max + (q - p.cm_row0) * 128 + lane;
+    const int64_t chunk_stride = p.cm_rows * 128;
     for (int g = 0; g < p.n_chunks; g += 8) {
       float w[8][4];
 #pragma unroll
@@ -712,7 +714,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_select_kernel(const PassPar
           ph ^= 1u;
         }
       }
-      float4* dst = reinterpret_cast<float4*>(p.class_max + ((int64_t)chunk * p.nq_pad + q) * 128 + (ew >> 2) * 32);
+      float4* dst = reinterpret_cast<float4*>(p.class_max + ((int64_t)chunk * p.cm_rows + (q - p.cm_row0)) * 128 + (ew >> 2) * 32);
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4)
         dst[j4] = make_float4(cmax[j4 * 4], cmax[j4 * 4 + 1], cmax[j4 * 4 + 2], cmax[j4 * 4 + 3]);
@@ -901,7 +903,9 @@ extern "C" int evavos_debug_trace_base(int i0) { return (int)cudaMemcpyToSymbol(
 #endif
 
 // Candidate generation for all queries: class maxima, thresholds and candidate lists in one cooperative launch
-// per wave of query tiles (one wave whenever n_query <= 128 * n_sm).
+// per wave of query tiles (one wave whenever n_query <= 128 * n_sm).  With more query tiles than SMs the full waves
+// run one CTA per tile over the whole bank, and the LAST, partial wave splits the bank into as many chunks as fit
+// the machine (319 tiles on 148 SMs: 148 + 148 + 23 tiles x 6 chunks = 2.17 sweeps' worth of time instead of 3).
 int launch_score_select(const float* query, int64_t query_ch_stride, const void* key_tiles, const float* key_maxnorm,
                         int64_t n_pos, int64_t n_query, int top_k, int n_chunks, int sample_stride, int n_sm,
                         float* class_max, float* tau, int2* cand, int32_t* cand_cnt, void* strip,
@@ -917,17 +921,29 @@ int launch_score_select(const float* query, int64_t query_ch_stride, const void*
   const int mt_total = (int)score_pass_mtiles(n_query);
   const int wave = n_sm / kCluster * kCluster;
   const int mt_per_launch = n_chunks > 1 ? mt_total : (mt_total < wave ? mt_total : wave);
-  for (int m0 = 0; m0 < mt_total; m0 += mt_per_launch) {
+  const int n_ktiles = (int)ceil_div(n_pos, kTilePos);
+  int tiles_w = 0;
+  for (int m0 = 0; m0 < mt_total; m0 += tiles_w) {
+    const int remaining = mt_total - m0;
+    int chunks_w = n_chunks;
+    tiles_w = remaining < mt_per_launch ? remaining : mt_per_launch;
+    if (n_chunks <= 1 && m0 > 0 && remaining < wave) {   // the partial last wave of a multi-wave read
+      chunks_w = wave / remaining;
+      if (chunks_w > n_ktiles) chunks_w = n_ktiles;
+      if (chunks_w < 1) chunks_w = 1;
+    }
     PassParams p;
     p.query = query;
     p.query_ch_stride = query_ch_stride;
     p.key_tiles = reinterpret_cast<const uint8_t*>(key_tiles);
     p.n_pos = n_pos;
     p.n_query = n_query;
-    p.n_mtiles = mt_total - m0 < mt_per_launch ? mt_total - m0 : mt_per_launch;
+    p.n_mtiles = tiles_w;
     p.nq_pad = (int64_t)mt_total * 128;
-    p.n_ktiles = (int)ceil_div(n_pos, kTilePos);
-    p.n_chunks = n_chunks;
+    p.cm_row0 = (int64_t)m0 * 128;
+    p.cm_rows = (int64_t)tiles_w * 128;     // chunks_w * tiles_w <= n_sm tile rows: inside the buffer api.cu carves
+    p.n_ktiles = n_ktiles;
+    p.n_chunks = chunks_w;
     p.sample_stride = sample_stride;
     p.class_max = class_max;
     p.tau = tau;
@@ -948,7 +964,7 @@ int launch_score_select(const float* query, int64_t query_ch_stride, const void*
       if (period > 1.0e6) period = 1.0e6;
       p.flush_period = (int)period;
     }
-    const unsigned grid = (unsigned)(p.n_mtiles * n_chunks);
+    const unsigned grid = (unsigned)(p.n_mtiles * chunks_w);
     // (all mt_total + 1 words: the word after the tile counters is the finalizer's overflow count, see api.cu)
     EVAVOS_CUDA_OK(cudaMemsetAsync(grid_counter, 0, sizeof(unsigned int) * (size_t)(mt_total + 1), st));
     // cooperative (the grid barrier needs every CTA resident) and, with EVAVOS_CLUSTER = 2, in clusters of two

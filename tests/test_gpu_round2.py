@@ -289,3 +289,29 @@ def test_overflow_count_is_zero_on_separable_scores():
     bank = ev.MemoryBank.from_tensors(mk.to(dev), mv.to(dev))
     ev.memory_read(bank, qk.to(dev), 50)
     assert last_overflow_count() == 0
+
+
+def test_more_query_tiles_than_sms():
+    """20 800 queries = 163 query tiles on 148 SMs: the filter runs one full wave (148 tiles, one CTA per tile over
+    the whole bank) and a partial wave whose 15 tiles split the bank into 9 chunks each - class maxima, thresholds
+    and lists of both waves must give the exact selection."""
+    import evavos_b200 as ev
+    from evavos_b200 import _lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(123)
+    t, h, w, frames = 2, 40, 40, 13
+    mk = torch.randn(1, 64, t, h, w, generator=g)
+    mv = torch.randn(1, 32, t, h, w, generator=g)
+    qk = torch.randn(1, 64, frames, h, w, generator=g)
+    bank = ev.MemoryBank.from_tensors(mk.to(dev), mv.to(dev))
+    out_t, aff_t = ev.memory_read(bank, qk.to(dev), 50, want_topk=True, path=_lib.PATH_TENSOR)
+    out_x, aff_x = ev.memory_read(bank, qk.to(dev), 50, want_topk=True, path=_lib.PATH_SIMT)
+    assert torch.equal(aff_t.idx, aff_x.idx)
+    assert torch.equal(aff_t.weight, aff_x.weight)
+    assert torch.equal(out_t, out_x)
+    # a sample of queries from both waves against the fp64 oracle
+    nq = frames * h * w
+    pick = np.r_[0:64, 148 * 128 - 32:148 * 128 + 96, nq - 64:nq]
+    s64 = onp.affinity_scores(mk[0].reshape(64, -1).numpy(), qk[0].reshape(64, -1)[:, pick].numpy())
+    exact, tie, bad, bad_q = onp.compare_topk(aff_t.idx.cpu().numpy()[pick], s64, 50, TIE_TOL)
+    assert bad == 0, bad_q[:5]
