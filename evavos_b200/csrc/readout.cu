@@ -39,9 +39,12 @@ __device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
 
 // fp32 rows; each CTA covers 128 * NV channels starting at blockIdx.z * 128 * NV of rows that are CV floats long.
 // grid (ceil(nq/8), K, CV / (128 * NV)), 256 threads.
-// QMAJOR: the output is (n_query, K, CV) - one contiguous K*CV row per query, written straight from the registers
-// (the layout the sharded read reduces over: a query slice is a contiguous chunk); out_*_stride are ignored.
-template <int NV, bool QMAJOR>
+// MODE 0: out[o][c][q] with object / channel strides (the reference layouts), transposed through shared memory.
+// MODE 1 (query-major): the output is (n_query, K, CV) - one contiguous K*CV row per query, written straight from the
+//         registers (the layout the sharded read reduces over: a query slice is a contiguous chunk); strides ignored.
+// MODE 2 (channels-last): out[frame][o][position][c] - an NHWC destination such as the decoder input of a
+//         channels_last engine; `out_ch_stride` carries the POSITION stride; also straight from the registers.
+template <int NV, int MODE>
 __global__ void __launch_bounds__(kRoThreads) readout_f32_kernel(
     const float* __restrict__ val_pm_all, int64_t capacity_pos, int CVfull, const int32_t* __restrict__ idx,
     const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out_all,
@@ -77,9 +80,17 @@ __global__ void __launch_bounds__(kRoThreads) readout_f32_kernel(
       }
     }
   }
-  if constexpr (QMAJOR) {
+  if constexpr (MODE != 0) {
     if (q < n_query) {
-      float* row = out_all + ((int64_t)q * gridDim.y + o) * CVfull + (int64_t)blockIdx.z * CV;
+      float* row;
+      if constexpr (MODE == 1) {
+        row = out_all + ((int64_t)q * gridDim.y + o) * CVfull + (int64_t)blockIdx.z * CV;
+      } else {
+        const uint32_t f = q_per_frame > 0 ? (uint32_t)q / (uint32_t)q_per_frame : 0u;
+        const uint32_t pos = (uint32_t)q - f * (uint32_t)q_per_frame;
+        row = out_all + (int64_t)f * frame_stride + (int64_t)o * out_obj_stride + (int64_t)pos * out_ch_stride +
+              (int64_t)blockIdx.z * CV;
+      }
 #pragma unroll
       for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(row + i * 128 + lane * 4) = acc[i];
     }
@@ -103,7 +114,7 @@ __global__ void __launch_bounds__(kRoThreads) readout_f32_kernel(
 }
 
 // bf16 rows, CV = 256 * NV (8 bf16 per 16-byte load), fp32 accumulation.
-template <int NV, bool QMAJOR>
+template <int NV, int MODE>
 __global__ void __launch_bounds__(kRoThreads) readout_bf16_kernel(
     const __nv_bfloat16* __restrict__ val_pm, int64_t capacity_pos, const int32_t* __restrict__ idx,
     const float* __restrict__ weight, int64_t n_query, int top_k, float* __restrict__ out,
@@ -147,9 +158,16 @@ __global__ void __launch_bounds__(kRoThreads) readout_bf16_kernel(
       }
     }
   }
-  if constexpr (QMAJOR) {
+  if constexpr (MODE != 0) {
     if (q < n_query) {
-      float* row = out + ((int64_t)q * gridDim.y + o) * CV;
+      float* row;
+      if constexpr (MODE == 1) {
+        row = out + ((int64_t)q * gridDim.y + o) * CV;
+      } else {
+        const uint32_t f = q_per_frame > 0 ? (uint32_t)q / (uint32_t)q_per_frame : 0u;
+        const uint32_t pos = (uint32_t)q - f * (uint32_t)q_per_frame;
+        row = out + (int64_t)f * frame_stride + (int64_t)o * out_obj_stride + (int64_t)pos * out_ch_stride;
+      }
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         *reinterpret_cast<float4*>(row + i * 256 + lane * 8) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
@@ -215,12 +233,24 @@ __global__ void scatter_dense_kernel(const int32_t* __restrict__ idx, const floa
 
 }  // namespace
 
-// out_ch_stride < 0 selects the query-major output (n_query, K, CV).
+// out_ch_stride < 0 selects the query-major output (n_query, K, CV); out_ch_stride == 1 a channels-last destination
+// whose position stride is out_obj_stride / (q_per_frame or n_query) (see include/evavos.h, readout_ch_stride).
 int launch_readout(const EvavosBankShadow& b, const int32_t* idx, const float* weight, int64_t n_query,
                    int top_k, float* out, int64_t out_obj_stride, int64_t out_ch_stride, int q_per_frame,
                    int64_t frame_stride, cudaStream_t st) {
   if (n_query <= 0) return EVAVOS_OK;
   const bool qmajor = out_ch_stride < 0;
+  const bool chlast = out_ch_stride == 1 && n_query > 1;   // (one query: both readings address the same elements)
+  if (chlast) {
+    const int64_t per_obj = q_per_frame > 0 ? q_per_frame : n_query;
+    if (out_obj_stride <= 0 || out_obj_stride % per_obj != 0 || (out_obj_stride / per_obj) % 4 != 0 ||
+        out_obj_stride / per_obj < b.CV || reinterpret_cast<uintptr_t>(out) % 16 != 0 || frame_stride % 4 != 0) {
+      set_error("readout: channels-last destination needs obj_stride = positions x (16-byte aligned row of >= CV floats)");
+      return EVAVOS_ERR_INVALID;
+    }
+    out_ch_stride = out_obj_stride / per_obj;     // from here on: the POSITION stride of the row kernels' MODE 2
+  }
+  const int mode = qmajor ? 1 : (chlast ? 2 : 0);
   if (out_ch_stride == 0) out_ch_stride = n_query;
   if (out_obj_stride == 0) out_obj_stride = (int64_t)b.CV * n_query;
   const dim3 grid((unsigned)ceil_div(n_query, kQPerCta), (unsigned)b.K);
@@ -229,12 +259,12 @@ int launch_readout(const EvavosBankShadow& b, const int32_t* idx, const float* w
   EVAVOS_CUDA_OK(launch_pdl(readout_f32_kernel<NV, QM>, dim3(grid.x, grid.y, SPLIT), dim3(kRoThreads), 0, st,        \
                             reinterpret_cast<const float*>(b.val_pm), b.capacity_pos, b.CV, idx, weight,      \
                             n_query, top_k, out, out_obj_stride, out_ch_stride, q_per_frame, frame_stride))
-#define EVAVOS_RO_F32(NV, SPLIT) do { if (qmajor) EVAVOS_RO_F32_(NV, SPLIT, true); else EVAVOS_RO_F32_(NV, SPLIT, false); } while (0)
+#define EVAVOS_RO_F32(NV, SPLIT) do { if (mode == 1) EVAVOS_RO_F32_(NV, SPLIT, 1); else if (mode == 2) EVAVOS_RO_F32_(NV, SPLIT, 2); else EVAVOS_RO_F32_(NV, SPLIT, 0); } while (0)
 #define EVAVOS_RO_BF16_(NV, QM)                                                                               \
   EVAVOS_CUDA_OK(launch_pdl(readout_bf16_kernel<NV, QM>, grid, dim3(kRoThreads), 0, st,                              \
                             reinterpret_cast<const __nv_bfloat16*>(b.val_pm), b.capacity_pos, idx, weight,    \
                             n_query, top_k, out, out_obj_stride, out_ch_stride, q_per_frame, frame_stride))
-#define EVAVOS_RO_BF16(NV) do { if (qmajor) EVAVOS_RO_BF16_(NV, true); else EVAVOS_RO_BF16_(NV, false); } while (0)
+#define EVAVOS_RO_BF16(NV) do { if (mode == 1) EVAVOS_RO_BF16_(NV, 1); else if (mode == 2) EVAVOS_RO_BF16_(NV, 2); else EVAVOS_RO_BF16_(NV, 0); } while (0)
   if (b.val_dtype == EVAVOS_F32 && row16 && b.CV % 128 == 0 && b.CV <= 512) {
     // Splitting a row's channels over two CTAs (more resident warps) was measured SLOWER on B200 (55 vs 42 us at
     // cfg2: twice the L2 requests at half the size), so one warp keeps a whole value row.
@@ -248,6 +278,9 @@ int launch_readout(const EvavosBankShadow& b, const int32_t* idx, const float* w
   } else if (b.val_dtype == EVAVOS_BF16 && row16 && b.CV % 256 == 0 && b.CV <= 512) {
     if (b.CV == 256) EVAVOS_RO_BF16(1);
     else EVAVOS_RO_BF16(2);
+  } else if (chlast) {
+    set_error("readout: a channels-last destination needs CV %% 128 == 0 (fp32) / CV %% 256 == 0 (bf16), CV <= 512");
+    return EVAVOS_ERR_UNSUPPORTED;
   } else {
     const dim3 g2((unsigned)n_query, (unsigned)b.K);
     if (b.val_dtype == EVAVOS_BF16)

@@ -257,7 +257,13 @@ class InferenceCore:
                 # The frames of a segment are independent given the bank: one read and one decoder pass for all of
                 # them.  The read kernel writes straight into the readout half of the decoder input (F,K,2*CV,H,W);
                 # the other half is the frames' query value feature - no torch.cat (prop_net.py:189-190).
-                m4 = torch.empty((len(seg), K, 2 * CV, H, W), dtype=torch.float32, device=self.device)
+                if self.channels_last:
+                    # NHWC engine: the decoder's first convolutions take the input as it is (no 33 MB layout conversion
+                    # per use), and the read kernel writes channel-contiguous rows straight from its accumulators
+                    m4 = torch.empty((len(seg) * K, 2 * CV, H, W), dtype=torch.float32, device=self.device,
+                                     memory_format=torch.channels_last).view(len(seg), K, 2 * CV, H, W)
+                else:
+                    m4 = torch.empty((len(seg), K, 2 * CV, H, W), dtype=torch.float32, device=self.device)
                 self._read(bank, qk, out=m4 if len(seg) > 1 else m4[0])
                 m4[:, :, CV:] = torch.cat([f[1] for f in feats], 0).unsqueeze(1)
                 decoded = self._conv.decode(m4, torch.cat([f[3] for f in feats], 0), torch.cat([f[4] for f in feats], 0))

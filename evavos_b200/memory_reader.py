@@ -118,11 +118,25 @@ def memory_read(bank: MemoryBank, qk: torch.Tensor, top_k: int = 50, n_frames: i
             out = torch.empty((bank.K, bank.CV, nq), dtype=torch.float32, device=dev)
         elif len(spatial) == 3 and out.dim() == 5 and tuple(out.shape) == (spatial[0], bank.K, out.shape[2]) + spatial[1:]:
             # frame-major (F, K, C>=CV, H, W): one destination block per query frame
-            if out.dtype != torch.float32 or out.device != dev or out.shape[2] < bank.CV or not out[0, 0, 0].is_contiguous():
-                raise ValueError(f"out {tuple(out.shape)} cannot receive a frame-major readout")
-            a.readout_obj_stride, a.readout_ch_stride = out.stride(1), out.stride(2)
-            a.queries_per_frame, a.readout_frame_stride = spatial[1] * spatial[2], out.stride(0)
+            hw_q = spatial[1] * spatial[2]
+            if out.dtype == torch.float32 and out.device == dev and out.shape[2] >= bank.CV and out.stride(2) == 1 \
+                    and hw_q > 1 and out.stride(4) == out.shape[2] and out.stride(3) == spatial[2] * out.shape[2] \
+                    and (bank.K == 1 or out.stride(1) == hw_q * out.shape[2]):
+                # ... whose (C, H, W) blocks are channels-last (the decoder input of an NHWC engine): the rows go out
+                # as they are accumulated, channel-contiguous (readout_ch_stride = 1, include/evavos.h)
+                a.readout_obj_stride, a.readout_ch_stride = hw_q * out.shape[2], 1
+            else:
+                if out.dtype != torch.float32 or out.device != dev or out.shape[2] < bank.CV or not out[0, 0, 0].is_contiguous():
+                    raise ValueError(f"out {tuple(out.shape)} cannot receive a frame-major readout")
+                a.readout_obj_stride, a.readout_ch_stride = out.stride(1), out.stride(2)
+            a.queries_per_frame, a.readout_frame_stride = hw_q, out.stride(0)
             frame_major = True
+        elif len(spatial) == 2 and out.dim() == 4 and out.dtype == torch.float32 and out.device == dev \
+                and out.shape[0] == bank.K and out.shape[1] >= bank.CV and tuple(out.shape[2:]) == spatial \
+                and out.stride(1) == 1 and nq > 1 and out.stride(3) == out.shape[1] \
+                and out.stride(2) == spatial[1] * out.shape[1] and (bank.K == 1 or out.stride(0) == nq * out.shape[1]):
+            # (K, C>=CV, H, W) in channels_last memory format
+            a.readout_obj_stride, a.readout_ch_stride = nq * out.shape[1], 1
         else:
             # (K, C>=CV, *spatial) fp32 with contiguous positions: the kernel takes object / channel strides
             if out.dtype != torch.float32 or out.device != dev or out.shape[0] != bank.K or out.shape[1] < bank.CV \

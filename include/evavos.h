@@ -135,7 +135,11 @@ typedef struct EvavosMemReadArgs {
   int64_t n_query;
   int64_t query_ch_stride;
   int64_t readout_obj_stride; /* elements between objects in `readout` (0 -> CV*n_query) */
-  int64_t readout_ch_stride;  /* elements between channels in `readout` (0 -> n_query)    */
+  int64_t readout_ch_stride;  /* elements between channels in `readout` (0 -> n_query).  1 = channels-last (NHWC)
+                                 destination: element (object o, channel c, position p) of a frame at
+                                 o * readout_obj_stride + p * P + c with the position stride
+                                 P = readout_obj_stride / (queries_per_frame or n_query) >= CV, P % 4 == 0
+                                 (fp32 CV % 128 == 0 / bf16 CV % 256 == 0 banks only)              */
   int32_t top_k;
   int32_t path;            /* EVAVOS_PATH_*                                           */
   int32_t n_sm;            /* SM count to size grids for (0 -> query the device)      */

@@ -315,3 +315,27 @@ def test_more_query_tiles_than_sms():
     s64 = onp.affinity_scores(mk[0].reshape(64, -1).numpy(), qk[0].reshape(64, -1)[:, pick].numpy())
     exact, tie, bad, bad_q = onp.compare_topk(aff_t.idx.cpu().numpy()[pick], s64, 50, TIE_TOL)
     assert bad == 0, bad_q[:5]
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_readout_into_a_channels_last_destination(bf16):
+    """The decoder input of an NHWC engine: (F, K, 2*CV, H, W) / (K, 2*CV, H, W) blocks in channels_last memory
+    format receive the readout channel-contiguously (readout_ch_stride = 1) - the same numbers as the plain layout."""
+    import evavos_b200 as ev
+    dev = torch.device("cuda:0")
+    K, CV, T, H, W, F = 2, 512, 3, 9, 14, 3
+    mk, _, mv = synth(77, 64, CV, T, H, W, K)
+    bank = ev.MemoryBank.from_tensors(mk.to(dev), mv.to(dev), value_dtype=torch.bfloat16 if bf16 else torch.float32)
+    g = torch.Generator().manual_seed(78)
+    qk5 = torch.randn(1, 64, F, H, W, generator=g).to(dev)
+    ref5, _ = ev.memory_read(bank, qk5, 50)                                   # (K, CV, F, H, W)
+    m4 = torch.full((F * K, 2 * CV, H, W), -7.0, device=dev).contiguous(memory_format=torch.channels_last).view(F, K, 2 * CV, H, W)
+    got5, _ = ev.memory_read(bank, qk5, 50, out=m4)
+    assert got5.data_ptr() == m4.data_ptr() and m4.stride(2) == 1
+    assert torch.equal(m4[:, :, :CV], ref5.permute(2, 0, 1, 3, 4))
+    assert (m4[:, :, CV:] == -7.0).all()                                      # the other half is not touched
+    qk4 = qk5[:, :, 1].contiguous()
+    ref4, _ = ev.memory_read(bank, qk4, 50)
+    o4 = torch.full((K, 2 * CV, H, W), -7.0, device=dev).contiguous(memory_format=torch.channels_last)
+    ev.memory_read(bank, qk4, 50, out=o4)
+    assert torch.equal(o4[:, :CV], ref4) and (o4[:, CV:] == -7.0).all()
