@@ -513,8 +513,30 @@ def run_cfg3(args, cfg, rank, world, local_rank):
     fps, ms, out = measure(channels_last=True, cuda_graphs=True)
     plain_fps, plain_ms, _ = measure(fold_bn=False)                      # the same engine without the conv rewrites
     amp_fps, amp_ms, _ = measure(amp=True, cuda_graphs=True)             # bf16 autocast variant (reduced precision)
+    untail_fps, untail_ms, _ = measure(channels_last=True, cuda_graphs=True, fused_tails=False)   # decoder tails in PyTorch
     if rank != 0:
         return
+    # the reference's stock loop on this GPU (oracle/stock_engine.py: frame by frame, dense affinity + topk + scatter,
+    # bmm per object, modules as they are) - what `InferenceCore.interact` of the reference does here before switching
+    try:
+        from oracle.stock_engine import StockEngine
+        n_ref = max(1, min(args.steps, 3))
+        StockEngine(prop, fuse, videos[0], k, device=dev).interact(mask, 0)
+        torch.cuda.synchronize(dev)
+        c0 = time.perf_counter()
+        for i in range(n_ref):
+            ref_masks = StockEngine(prop, fuse, videos[i % 2], k, device=dev).interact(mask, 0)
+        torch.cuda.synchronize(dev)
+        ref_dt = (time.perf_counter() - c0) / n_ref
+        last = (args.steps - 1) % 2
+        if (n_ref - 1) % 2 != last:
+            ref_masks = StockEngine(prop, fuse, videos[last], k, device=dev).interact(mask, 0)
+        gpu_base = {"value": (t - 1) / ref_dt, "unit": "frames/s", "ms_per_step": 1e3 * ref_dt, "videos": n_ref,
+                    "kind": "port of the reference's InferenceCore loop on CUDA tensors (oracle/stock_engine.py), 1 GPU",
+                    "speedup": fps / world / ((t - 1) / ref_dt),
+                    "mask_agreement": float((torch.as_tensor(ref_masks) == torch.as_tensor(out).cpu()).float().mean())}
+    except Exception as e:
+        gpu_base = {"unavailable": repr(e)[:200]}
     from evavos_b200.conv_opt import conv_passes
     line = {
         "metric": "propagated frames/sec (end-to-end interact)", "value": fps, "unit": "frames/s",
@@ -522,13 +544,15 @@ def run_cfg3(args, cfg, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (cuDNN TF32 convolutions, fp32 keys / values / memory read)",
         "data": "synthetic", "config": {"workload": args.workload + ": " + desc, "frames": t, "image": [h, w], "mem_freq": 5,
-                                         "engine": "fold_bn + fused conv-bias-ReLU, channels_last, cuda_graphs",
+                                         "engine": "fold_bn + fused conv-bias-ReLU, channels_last, cuda_graphs, fused decoder tails",
                                          "fused_conv_ops": bool(conv_passes(prop, False, True, True, True).fused),
                                          "note": "wall clock incl. H2D of the video and D2H of the masks; random weights "
                                                  "(every candidate list overflows: the exact tiled pass runs on every read)"},
         "mask_shape": list(out.shape),
         "plain_engine": {"value": plain_fps, "ms_per_step": plain_ms,
                          "note": "fold_bn=False, NCHW, no graphs: PyTorch modules as they are around the same memory read"},
+        "gpu_baseline": gpu_base,
+        "without_fused_decoder_tails": {"value": untail_fps, "ms_per_step": untail_ms},
         "amp_variant": {"value": amp_fps, "ms_per_step": amp_ms, "dtype": "bf16 autocast convolutions (reduced precision: "
                         "not the headline), fp32 keys / values / memory read"},
     }

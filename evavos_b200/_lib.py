@@ -81,6 +81,8 @@ SIGNATURES = {
     "evavos_jf_metrics": (_c_i32, [_c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_i32, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp]),
     "evavos_affinity_dense": (_c_i32, [_c_vp, _c_vp, _c_i64, _c_i32, _c_i64, _c_vp, _c_vp]),
     "evavos_aggregate_wbg": (_c_i32, [_c_vp, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_vp]),
+    "evavos_bias_residual_nhwc": (_c_i32, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_i32, _c_vp]),
+    "evavos_upsample2x_add_nhwc": (_c_i32, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_i32, _c_i32, _c_vp]),
     "evavos_argmax_unpad": (_c_i32, [_c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_vp, _c_vp, _c_i32, _c_i32, _c_i32, _c_i32, _c_vp]),
     "evavos_attention_workspace_bytes": (ctypes.c_size_t, [_c_i32, _c_i64, _c_i64, _c_i32]),
     "evavos_attention_readout": (_c_i32, [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_i32, _c_i32, _c_i64, _c_i64,

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libevavos_sm100.so")
-SOURCES = ["api.cu", "bank.cu", "select_simt.cu", "score_tc.cu", "readout.cu", "aggregate.cu", "merge.cu", "argmax.cu", "attention.cu", "peer.cu", "metrics.cu", "select_dense.cu"]
+SOURCES = ["api.cu", "bank.cu", "select_simt.cu", "score_tc.cu", "readout.cu", "aggregate.cu", "merge.cu", "argmax.cu", "attention.cu", "peer.cu", "metrics.cu", "select_dense.cu", "decoder_ops.cu"]
 HEADERS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")) + \
           [os.path.join(os.path.dirname(HERE), "include", "evavos.h")]
 NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",

@@ -139,6 +139,75 @@ class FoldedValueEncoder(_FoldedTrunk):
         return e.fuser(x, key_f16)
 
 
+class FusedDecoder(nn.Module):
+    """``PropagationNetwork.decode_input`` (prop_net.py:13-30, batched over frames and objects) on a private NHWC copy of
+    the decoder in ``dtype``.  The decoder has no normalisation layers to fold; what sits between its convolutions is
+    bias adds, residual adds, ReLUs and two bilinear x2 upsamplings, one PyTorch kernel each over up to 5 x 256 x 120 x
+    216 elements.  Here every convolution that feeds a ReLU is a fused cuDNN conv-bias-ReLU, the others run without
+    bias, and the tails are the two in-place kernels of csrc/decoder_ops.cu:
+
+        ResBlock        x + conv2(relu(conv1(relu(x))))        -> bias_residual_(conv2', b2 (+ b_ds), x or downsample'(x))
+        UpsampleBlock   skip_conv(skip) + up2x(x)              -> upsample2x_add_(skip_conv', b_skip, x)
+
+    (primes: without bias).  The ReLU in front of ``pred`` rides on the last ResBlock's tail."""
+
+    def __init__(self, dec: nn.Module, dtype):
+        super().__init__()
+        self.dec = copy.deepcopy(dec).eval().requires_grad_(False).to(memory_format=torch.channels_last).to(dtype)
+        self.dtype = dtype
+        self.fused = _probe_fused(next(dec.parameters()).device, dtype, True)
+        for name, rb in (("compress", dec.compress), ("up_16_8", dec.up_16_8.out_conv), ("up_8_4", dec.up_8_4.out_conv)):
+            b = rb.conv2.bias.detach().float()
+            if rb.downsample is not None:
+                b = b + rb.downsample.bias.detach().float()
+            self.register_buffer("res_bias_" + name, b.contiguous().clone())
+        for name in ("up_16_8", "up_8_4"):
+            self.register_buffer("skip_bias_" + name, getattr(dec, name).skip_conv.bias.detach().float().contiguous().clone())
+
+    def _in(self, x):
+        return x.to(self.dtype).contiguous(memory_format=torch.channels_last)
+
+    @staticmethod
+    def _bare(conv, x):
+        y = torch.nn.functional.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+        return y.contiguous(memory_format=torch.channels_last)       # (a no-op: cuDNN answers NHWC inputs in NHWC)
+
+    def _res(self, rb, x, bias, relu_out=False):
+        from .decoder_ops import bias_residual_
+        a = torch.relu(x)
+        c1 = _conv_relu(rb.conv1, a) if self.fused else torch.relu(rb.conv1(a))
+        idt = x if rb.downsample is None else self._bare(rb.downsample, x)
+        return bias_residual_(self._bare(rb.conv2, c1), bias, idt, relu=relu_out)
+
+    def _up(self, blk, skip, x, k, skip_bias, res_bias, relu_out=False):
+        from .decoder_ops import upsample2x_add_
+        s = self._bare(blk.skip_conv, skip)
+        if k != 1:      # the per-frame skip feature, once per object (the reference broadcasts it in the add)
+            s = s.repeat_interleave(k, 0).contiguous(memory_format=torch.channels_last)
+        return self._res(blk.out_conv, upsample2x_add_(s, skip_bias, x), res_bias, relu_out)
+
+    def forward(self, m4, qf8, qf4):
+        f, k, _, hh, ww = m4.shape
+        d = self.dec
+        with torch.autocast("cuda", enabled=False):
+            x = self._res(d.compress, self._in(m4.reshape(f * k, -1, hh, ww)), self.res_bias_compress)
+            x = self._up(d.up_16_8, self._in(qf8), x, k, self.skip_bias_up_16_8, self.res_bias_up_16_8)
+            x = self._up(d.up_8_4, self._in(qf4), x, k, self.skip_bias_up_8_4, self.res_bias_up_8_4, relu_out=True)
+            x = torch.nn.functional.interpolate(d.pred(x).float(), scale_factor=4, mode="bilinear", align_corners=False)
+            return torch.sigmoid(x).view(f, k, 1, *x.shape[-2:])
+
+
+def fused_decoder(prop_net: nn.Module, dtype=torch.float32) -> FusedDecoder:
+    """The FusedDecoder of ``prop_net.decoder``; cached on ``prop_net`` like the folded encoders."""
+    stamp = _stamp((prop_net.decoder,), (dtype,))
+    slot = prop_net.__dict__.setdefault("_evavos_decoder", _CacheSlot())
+    if slot.stamp != stamp:
+        with torch.no_grad():
+            slot.value = FusedDecoder(prop_net.decoder, dtype)
+        slot.stamp = stamp
+    return slot.value
+
+
 def _stamp(mods, extra):
     tensors = [t for m in mods for t in list(m.parameters()) + list(m.buffers())]
     first = tensors[0]
@@ -184,7 +253,7 @@ class ConvPasses:
     engine that holds it is alive (in-place updates are fine without graphs, and with them as long as ``fold_bn`` is
     off - a folded copy is a snapshot)."""
 
-    def __init__(self, prop_net, amp, channels_last, fold_bn, cuda_graphs):
+    def __init__(self, prop_net, amp, channels_last, fold_bn, cuda_graphs, fused_tails=True):
         self.amp, self.channels_last, self.fold_bn, self.cuda_graphs = amp, channels_last, fold_bn, cuda_graphs
         dtype = torch.bfloat16 if amp else torch.float32
         ke, ve = folded_encoders(prop_net, channels_last, dtype) if fold_bn else (None, None)
@@ -201,7 +270,13 @@ class ConvPasses:
             # the memory key (and everything the read touches) stays fp32; the skip features keep the conv dtype
             return (outs[0].float(),) + tuple(outs[1:])
 
+        # NHWC engine with private weight copies: the decoder's elementwise tails run in csrc/decoder_ops.cu
+        fd = fused_decoder(prop_net, dtype) if fold_bn and channels_last and fused_tails else None
+        self.fused_decoder = fd is not None
+
         def decode(m4, qf8, qf4):
+            if fd is not None:
+                return fd(m4, qf8, qf4).float()
             with autocast():
                 return prop_net.decode_input(m4, qf8, qf4).float()
 
@@ -221,10 +296,11 @@ class ConvPasses:
             self.encode_key, self.decode, self.encode_value = encode_key, decode, encode_value
 
 
-def conv_passes(prop_net, amp=False, channels_last=False, fold_bn=True, cuda_graphs=False) -> ConvPasses:
+def conv_passes(prop_net, amp=False, channels_last=False, fold_bn=True, cuda_graphs=False, fused_tails=True) -> ConvPasses:
     """The ConvPasses of ``prop_net`` for these options; cached on ``prop_net`` (captured graphs are worth keeping
-    across the InferenceCores of a dataset) and rebuilt when its parameters were written, moved or re-laid-out."""
-    opts = (bool(amp), bool(channels_last), bool(fold_bn), bool(cuda_graphs))
+    across the InferenceCores of a dataset) and rebuilt when its parameters were written, moved or re-laid-out.
+    ``fused_tails``: with ``fold_bn`` and ``channels_last``, decode through FusedDecoder."""
+    opts = (bool(amp), bool(channels_last), bool(fold_bn), bool(cuda_graphs), bool(fused_tails))
     stamp = _stamp((prop_net,), opts)
     slot = prop_net.__dict__.setdefault("_evavos_passes", _CacheSlot(value={}))
     if slot.value is None:

@@ -523,6 +523,30 @@ int evavos_aggregate_wbg(const float* prob, float* out, int32_t K, int64_t npix,
   return launch_aggregate(prob, out, K, npix, keep_bg, hard, (cudaStream_t)stream);
 }
 
+int evavos_bias_residual_nhwc(void* y, const float* bias, const void* residual, int64_t rows, int32_t C, int32_t dtype,
+                              int32_t relu, evavos_stream_t stream) {
+  const int vec = dtype == EVAVOS_BF16 ? 8 : 4;
+  if (!y || !bias || rows < 0 || C <= 0 || C % vec != 0 || (dtype != EVAVOS_F32 && dtype != EVAVOS_BF16) ||
+      reinterpret_cast<uintptr_t>(y) % 16 != 0 || (residual && reinterpret_cast<uintptr_t>(residual) % 16 != 0) ||
+      reinterpret_cast<uintptr_t>(bias) % 16 != 0) {
+    set_error("bias_residual_nhwc: bad arguments (16-byte aligned channel-contiguous rows, C %% %d == 0)", vec);
+    return EVAVOS_ERR_INVALID;
+  }
+  return launch_bias_residual(y, bias, residual, rows, C, dtype == EVAVOS_BF16, relu, (cudaStream_t)stream);
+}
+
+int evavos_upsample2x_add_nhwc(void* y, const float* bias, const void* x, int64_t n, int32_t H, int32_t W, int32_t C,
+                               int32_t dtype, evavos_stream_t stream) {
+  const int vec = dtype == EVAVOS_BF16 ? 8 : 4;
+  if (!y || !bias || !x || n < 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || C <= 0 || C % vec != 0 ||
+      (dtype != EVAVOS_F32 && dtype != EVAVOS_BF16) || reinterpret_cast<uintptr_t>(y) % 16 != 0 ||
+      reinterpret_cast<uintptr_t>(x) % 16 != 0 || reinterpret_cast<uintptr_t>(bias) % 16 != 0) {
+    set_error("upsample2x_add_nhwc: bad arguments (even H, W; 16-byte aligned NHWC tensors, C %% %d == 0)", vec);
+    return EVAVOS_ERR_INVALID;
+  }
+  return launch_upsample2x_add(y, bias, x, n, H, W, C, dtype == EVAVOS_BF16, (cudaStream_t)stream);
+}
+
 int evavos_argmax_unpad(const float* prob, int32_t C, int64_t T, int32_t nh, int32_t nw, uint8_t* masks, uint8_t* out,
                         int32_t pad_top, int32_t pad_left, int32_t h, int32_t w, evavos_stream_t stream) {
   if (!prob || C <= 0 || C > 255 || T < 0 || nh <= 0 || nw <= 0 || (!masks && !out) ||

@@ -136,6 +136,8 @@ int launch_overflow_exact(const float* key_pm, const float* query, int64_t query
                           const unsigned int* overflow_cnt, const float* key_maxnorm, int32_t* out_idx,
                           float* out_weight, float* out_score, const EvavosPeers* peers, int64_t peer_gather_offset,
                           int n_sm, cudaStream_t st);
+int launch_bias_residual(void* y, const float* bias, const void* r, int64_t rows, int C, int bf16, int relu, cudaStream_t st);
+int launch_upsample2x_add(void* y, const float* bias, const void* x, int64_t n, int H, int W, int C, int bf16, cudaStream_t st);
 size_t jf_workspace_bytes(int64_t T, int h, int w);
 int launch_jf_metrics(const uint8_t* pred, const uint8_t* gt, int64_t T, int h, int w, int radius, void* workspace,
                       double* out, int32_t* gt_empty, cudaStream_t st);

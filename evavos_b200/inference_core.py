@@ -41,14 +41,16 @@ class InferenceCore:
     """
 
     def __init__(self, prop_net, fuse_net, images, num_objects, mem_profile=0, mem_freq=5, device="cuda", *,
-                 amp=False, fold_bn=True, channels_last=None, cuda_graphs=False):
+                 amp=False, fold_bn=True, channels_last=None, cuda_graphs=False, fused_tails=True):
         """Keywords of this engine, not of the reference:
         ``amp``: run the conv encoders / decoder under bf16 autocast; keys, values and the memory read stay fp32.
         ``fold_bn``: run the two ResNet encoders through BatchNorm-folded copies (conv_opt.py; ``prop_net`` itself is
         not modified; only with this package's PropagationNetwork).
         ``channels_last``: NHWC conv stacks (default: same as ``amp``).
         ``cuda_graphs``: capture the key encoder, decoder and value encoder once per input shape and replay them
-        (graphs.py; this package's PropagationNetwork only).  The graphs are cached on ``prop_net``."""
+        (graphs.py; this package's PropagationNetwork only).  The graphs are cached on ``prop_net``.
+        ``fused_tails``: with ``fold_bn`` and ``channels_last``, the decoder's bias / residual / ReLU / upsample tails
+        run in the two kernels of csrc/decoder_ops.cu (conv_opt.FusedDecoder) instead of one PyTorch kernel each."""
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("evavos_b200.InferenceCore needs a CUDA device: the memory read has no CPU path")
@@ -65,6 +67,7 @@ class InferenceCore:
         ours = hasattr(prop_net, "decode_input")
         self.fold_bn = bool(fold_bn) and ours and not prop_net.training
         self.cuda_graphs = bool(cuda_graphs) and ours
+        self.fused_tails = bool(fused_tails)
 
         if mem_profile == 0:
             self.data_dev, self.result_dev, self.k_buf_size, self.i_buf_size = dev, dev, 105, -1
@@ -150,7 +153,7 @@ class InferenceCore:
         if c is None:
             from .conv_opt import conv_passes
             c = self.__dict__["_conv_cache"] = conv_passes(self.prop_net, self.amp, self.channels_last, self.fold_bn,
-                                                           self.cuda_graphs)
+                                                           self.cuda_graphs, self.__dict__.get("fused_tails", True))
         return c
 
     def __getstate__(self):

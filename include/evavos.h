@@ -212,6 +212,20 @@ int evavos_aggregate_wbg(const float* prob, float* out, int32_t K, int64_t npix,
                          int32_t hard, evavos_stream_t stream);
 
 /*
+ * Fused elementwise tails of the decoder's convolutions (prop_net.py:13-30; modules.py ResBlock / UpsampleBlock), on
+ * channels-last tensors of `dtype` EVAVOS_F32 or EVAVOS_BF16, in place on `y`:
+ *   evavos_bias_residual_nhwc   y[row][c] = [relu](y + bias[c] (+ residual[row][c]))
+ *   evavos_upsample2x_add_nhwc  y[n][h][w][c] = y + bias[c] + bilinear_x2(x)[n][h][w][c], x of shape (n, H/2, W/2, C),
+ *                               F.interpolate(scale_factor=2, mode="bilinear", align_corners=False)
+ * bias is fp32 (C); all pointers 16-byte aligned; C % 4 == 0 (fp32) / C % 8 == 0 (bf16).  They replace the separate
+ * broadcast-add / add / upsample kernels PyTorch launches after F.conv2d (no reference counterpart beyond those ops).
+ */
+int evavos_bias_residual_nhwc(void* y, const float* bias, const void* residual, int64_t rows, int32_t C, int32_t dtype,
+                              int32_t relu, evavos_stream_t stream);
+int evavos_upsample2x_add_nhwc(void* y, const float* bias, const void* x, int64_t n, int32_t H, int32_t W, int32_t C,
+                               int32_t dtype, evavos_stream_t stream);
+
+/*
  * Hard masks of all frames in one pass (replaces the per-frame torch.argmax loop, the un-padding slices and the
  * contiguous copy of mivos/inference_core.py:247-257).  prob: (C, T, nh, nw) fp32, C <= 255.
  *   masks: (T, nh, nw) uint8 channel argmax (first maximal channel), or NULL

@@ -96,3 +96,41 @@ def test_staging_falls_back_for_small_and_cpu_tensors():
     t = torch.arange(12, dtype=torch.uint8).view(3, 4)
     out = download_numpy(t)
     assert out.shape == (3, 4) and (out == t.numpy()).all()
+
+
+@pytest.mark.parametrize("k", [1, 3])
+def test_fused_decoder_is_the_same_graph(prop, k, monkeypatch):
+    """conv_opt.FusedDecoder restructures decode_input (bias-free convolutions + two in-place tails); with torch doubles
+    for the two CUDA kernels (the GPU suite checks the kernels themselves) it is the same function on CPU."""
+    import torch.nn.functional as F
+
+    from evavos_b200 import decoder_ops
+    from evavos_b200.conv_opt import FusedDecoder, fused_decoder
+
+    def bias_residual_(y, bias, residual=None, relu=False):
+        assert y.is_contiguous(memory_format=torch.channels_last) and bias.dtype == torch.float32
+        y += bias.view(1, -1, 1, 1)
+        if residual is not None:
+            y += residual
+        return y.relu_() if relu else y
+
+    def upsample2x_add_(y, bias, x):
+        assert y.is_contiguous(memory_format=torch.channels_last) and x.is_contiguous(memory_format=torch.channels_last)
+        y += bias.view(1, -1, 1, 1) + F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+        return y
+
+    monkeypatch.setattr(decoder_ops, "bias_residual_", bias_residual_)
+    monkeypatch.setattr(decoder_ops, "upsample2x_add_", upsample2x_add_)
+    g = torch.Generator().manual_seed(5)
+    f, hh, ww = 2, 3, 5
+    m4 = torch.randn(f, k, 1024, hh, ww, generator=g)
+    qf8, qf4 = torch.randn(f, 512, 2 * hh, 2 * ww, generator=g), torch.randn(f, 256, 4 * hh, 4 * ww, generator=g)
+    want = prop.decode_input(m4, qf8, qf4)
+    fd = FusedDecoder(prop.decoder, torch.float32)
+    got = fd(m4, qf8, qf4)
+    assert got.shape == want.shape == (f, k, 1, 16 * hh, 16 * ww)
+    assert (got - want).abs().max().item() < 1e-5
+    assert not fd.fused                                             # no cuDNN on the CPU: the unfused conv + ReLU form
+    assert fused_decoder(prop) is fused_decoder(prop)               # cached on the network ...
+    assert "_evavos_decoder" not in prop.state_dict() and len(prop.state_dict()) == 405
+    assert copy.deepcopy(prop).__dict__["_evavos_decoder"].value is None    # ... and not copied with it

@@ -133,3 +133,30 @@ def test_jf_restatement_reproduces_reference_metrics():
                 assert jf_np.f_measure(pred[f], gt[f]) == g[f"{name}_f"][f]
             else:
                 assert g[f"{name}_jf"][f] == 20
+
+
+@pytest.mark.parametrize("tag", ["e2e_k1", "e2e_k2"])
+def test_stock_engine_matches_reference(tag):
+    """oracle/stock_engine.py (bench.py's cfg3 `gpu_baseline`) replays the interactions the live reference InferenceCore
+    recorded into tests/golden/e2e_*.npz - both on CPU, same op sequence: probabilities to 1e-5, masks equal except
+    where the reference itself is undecided."""
+    import evavos_b200 as ev
+    from evavos_b200.networks import seeded_init
+    from oracle.stock_engine import StockEngine
+    g = load(f"{tag}.npz")
+    with torch.no_grad():
+        prop, fuse = ev.PropagationNetwork().eval(), ev.FusionNet().eval()
+        seeded_init(prop, 1001)
+        seeded_init(fuse, 1002)
+        eng = StockEngine(prop, fuse, torch.from_numpy(g["images"]), int(g["num_objects"]), mem_freq=int(g["mem_freq"]),
+                          device="cpu")
+        assert tuple(eng.pad) == tuple(int(x) for x in g["pad"])
+        for n in range(int(g["n_interactions"])):
+            out = eng.interact(torch.from_numpy(g[f"mask_{n}"]), int(g[f"frame_{n}"]), scribble=bool(g[f"scribble_{n}"]))
+            ref_prob, ref_masks = g[f"prob_{n}"], g[f"np_masks_{n}"]
+            assert np.abs(eng.prob.numpy() - ref_prob).max() < 1e-5
+            srt = np.sort(ref_prob, 0)
+            lw, uw, lh, uh = (int(x) for x in g["pad"])
+            undecided = (srt[-1] - srt[-2] < 1e-5)[:, 0]
+            undecided = undecided[:, lh:undecided.shape[1] - uh or None, lw:undecided.shape[2] - uw or None]
+            assert out.shape == ref_masks.shape and not ((out != ref_masks) & ~undecided).any()
