@@ -14,8 +14,19 @@ pytestmark = pytest.mark.gpu
 ATOL = 2e-6
 
 
+@pytest.fixture(params=["auto", "simt", "tensor"])
+def form(request, monkeypatch):
+    """Both forms of the partial pass on every shape: CUDA cores (fp32) and tensor cores (3 x TF32 mma.sync); "auto" is
+    the size rule of csrc/attention.cu."""
+    if request.param == "auto":
+        monkeypatch.delenv("EVAVOS_ATTENTION_PATH", raising=False)
+    else:
+        monkeypatch.setenv("EVAVOS_ATTENTION_PATH", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("name", ["b2", "b4_peaky", "b1_flat"])
-def test_get_attention_golden(name):
+def test_get_attention_golden(name, form):
     """PropagationNetwork.get_attention on the GPU vs the reference's get_attention (tests/golden/attention.npz)."""
     g = load("attention.npz")
     dev = torch.device("cuda:0")
@@ -34,8 +45,8 @@ def test_get_attention_golden(name):
 
 
 @pytest.mark.parametrize("shape,n_vec,scale", [((30, 54), 8, 1.0), ((30, 54), 2, 3.0), ((68, 120), 12, 1.0),
-                                               ((5, 7), 33 - 1, 1.0), ((1, 3), 1, 1.0)])
-def test_attention_vs_oracle(shape, n_vec, scale):
+                                               ((5, 7), 33 - 1, 1.0), ((1, 3), 1, 1.0), ((48, 90), 5, 1.5)])
+def test_attention_vs_oracle(shape, n_vec, scale, form):
     """Full sizes (480p: 1620 x 1620; 1080p: 8160 x 8160), ragged tiny grids, up to the 32-row limit."""
     h, w = shape
     g = torch.Generator().manual_seed(77 + h)
@@ -54,7 +65,7 @@ def test_attention_vs_oracle(shape, n_vec, scale):
     assert np.abs(ones - 1).max() < 1e-6
 
 
-def test_attention_strided_inputs_and_errors():
+def test_attention_strided_inputs_and_errors(form):
     """Channel-strided views (a frame sliced out of a (1,CK,T,H,W) bank) are read in place; bad shapes fail loudly."""
     g = torch.Generator().manual_seed(5)
     bank = torch.randn(1, 64, 3, 6, 9, generator=g).cuda()
