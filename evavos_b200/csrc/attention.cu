@@ -9,8 +9,8 @@
 //    territory;
 //  * tensor cores (attention_partial_tc_kernel) for large maps (8.5 GF at 1080p, 68 x 120): warp-level
 //    mma.sync.m16n8k16 on fp16 halves with the error-compensated three-product split
-//    a.b ~ a_hi.b_hi + (a_lo.b_hi + a_hi.b_lo) / 2048  (hi = fp16(x), lo = fp16((x - hi) * 2048), every vector first
-//    scaled into fp16 range by an exact power of two: what is dropped is ~2^-22 relative, fp32-level), fp32
+//    a.b ~ a_hi.b_hi + (a_lo.b_hi + a_hi.b_lo)  (hi = fp16(x), lo = fp16(x - hi), every vector first normalised
+//    into fp16 range by an exact power of two: what is dropped is ~2^-22 relative, fp32-level), fp32
 //    accumulation, the online softmax on the accumulator fragments.  This is the legacy tensor path (HMMA), not
 //    tcgen05: the op is a few hundred microseconds a few times per interaction, and a register-resident
 //    flash-style softmax maps directly onto the mma.sync fragment layout.
@@ -120,20 +120,22 @@ constexpr int kTcQueries = 64;
 constexpr int kTcTile = 64;       // memory positions per shared-memory tile
 constexpr int kTcLd = 72;         // row stride (words): 72 = 8 mod 32 -> a B-fragment load (4 pair-rows x 8 positions) hits 32 banks
 
-// x = hi + lo / 2048 with hi = fp16(x), lo = fp16((x - hi) * 2048): 22 significant bits, what is dropped is ~2^-22 |x|.
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits for elements near the vector's largest (every
+// vector is first normalised so that its largest magnitude sits at 2^14, see range_factors); smaller elements keep an
+// ABSOLUTE error below 2^-25 of that, far inside what an fp32 dot product of the same vectors carries.
 __device__ __forceinline__ void split_pair(float xa, float xb, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(xa, xb);
   const float2 f = __half22float2(h);
-  const __half2 l = __floats2half2_rn((xa - f.x) * 2048.f, (xb - f.y) * 2048.f);
+  const __half2 l = __floats2half2_rn(xa - f.x, xb - f.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// Power-of-two factors that bring a vector whose largest magnitude is mx below 2^15 (fp16 range) and back: exact
-// scalings, 1.0 for ordinary keys.
+// Exact power-of-two factors that move a vector whose largest magnitude is mx to [2^14, 2^15) - inside fp16 range with
+// the low halves well above its subnormals - and back.
 __device__ __forceinline__ void range_factors(float mx, float& down, float& up) {
-  const int ex = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127;
-  const int e = ex > 14 ? ex - 14 : 0;
+  int e = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127 - 14;
+  e = e < -100 ? -100 : e;   // (zero / denormal vectors; the exponent field of mx is at most 254, so e <= 113)
   down = __uint_as_float((uint32_t)(127 - e) << 23);
   up = __uint_as_float((uint32_t)(127 + e) << 23);
 }
@@ -166,12 +168,14 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const float* src, bool
 // the warp's 16 query keys, hi and lo halves in registers for the whole kernel), columns are memory positions (B = the
 // key tile in shared memory).  The raw fp32 tile of step k+1 arrives by cp.async in a staging buffer while step k is
 // computed; between the steps the CTA splits it once into packed fp16 hi / lo pair-rows.  Products: hi.hi in one
-// accumulator, lo.hi + hi.lo (scaled by 2048) in another - a.b to ~2^-22, fp32-level.  A lane owns 2 queries x 2
+// accumulator, lo.hi + hi.lo in another - a.b to ~2^-22, fp32-level.  A lane owns 2 queries x 2
 // positions of every 16 x 8 score tile and keeps its own online-softmax state for them; the four lanes of a quad are
 // merged once at the end.  Scores are kept in log2 units (scale2 = log2(e) / sqrt(CK)): the exponentials are bare ex2.
 // part: as attention_partial_kernel, the max in log2 units.
+constexpr int tc_ctas_per_sm(int cp) { return cp <= 4 ? 4 : 3; }   // (registers: 128 / 152 / 168 per thread)
+
 template <int CP>
-__global__ void __launch_bounds__(kTcThreads, 3) attention_partial_tc_kernel(
+__global__ void __launch_bounds__(kTcThreads, tc_ctas_per_sm(CP)) attention_partial_tc_kernel(
     const float* __restrict__ mk, int64_t mk_ch_stride, const float* __restrict__ qk, int64_t qk_ch_stride,
     const float* __restrict__ vec, int64_t vec_row_stride, int n_vec, int64_t n_mem, int64_t n_query, float scale2,
     float* __restrict__ part) {
@@ -308,8 +312,8 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_partial_tc_kernel(
 #pragma unroll
         for (int h = 0; h < 2; ++h) {   // h = 0: query g (d0, d1), h = 1: query g + 8 (d2, d3)
           const float ts = h ? ts1 : ts0;
-          const float sa = fmaf(fmaf(cco[u][2 * h], 1.0f / 2048.f, chh[u][2 * h]), ts, -nr0);
-          const float sb = fmaf(fmaf(cco[u][2 * h + 1], 1.0f / 2048.f, chh[u][2 * h + 1]), ts, -nr1);
+          const float sa = fmaf(chh[u][2 * h] + cco[u][2 * h], ts, -nr0);
+          const float sb = fmaf(chh[u][2 * h + 1] + cco[u][2 * h + 1], ts, -nr1);
           const float mxs = fmaxf(sa, sb);
           if (mxs > run_max[h]) {
             const float r = ex2(run_max[h] - mxs);
@@ -408,10 +412,10 @@ int launch_cp(const float* mk, int64_t mk_ch_stride, const float* qk, int64_t qk
   return EVAVOS_OK;
 }
 
-int pick_splits_tc(int64_t n_mem, int64_t n_query, int n_sm) {
-  // Splits are runs of whole tiles; 3 CTAs fit an SM (registers).  Take the split count that leaves the fewest CTA slots
-  // idle in the last wave, lightly preferring fewer splits (each CTA sets up its query fragments once).
-  const int64_t q_blocks = ceil_div(n_query, kTcQueries), slots = (int64_t)n_sm * 3;
+int pick_splits_tc(int64_t n_mem, int64_t n_query, int n_sm, int ctas_per_sm) {
+  // Splits are runs of whole tiles.  Take the split count that leaves the fewest CTA slots idle in the last wave, lightly
+  // preferring fewer splits (each CTA sets up its query fragments once).
+  const int64_t q_blocks = ceil_div(n_query, kTcQueries), slots = (int64_t)n_sm * ctas_per_sm;
   int64_t max_s = ceil_div(n_mem, kTcTile) / 2;          // at least two tiles per split
   if (max_s > 32) max_s = 32;
   int best = 1;
@@ -450,7 +454,8 @@ int launch_tc(const float* mk, int64_t mk_ch_stride, const float* qk, int64_t qk
 size_t attention_workspace_bytes(int n_vec, int64_t n_mem, int64_t n_query, int n_sm) {
   // (whichever form runs: the tensor form carries at most 16 rows per pass)
   const size_t simt = (size_t)pick_splits(n_mem, n_query, n_sm) * (size_t)(padded_vecs(n_vec) + 2);
-  const size_t tc = (size_t)pick_splits_tc(n_mem, n_query, n_sm) * (size_t)(padded_vecs(n_vec < 16 ? n_vec : 16) + 2);
+  const int s3 = pick_splits_tc(n_mem, n_query, n_sm, 3), s4 = pick_splits_tc(n_mem, n_query, n_sm, 4);
+  const size_t tc = (size_t)(s3 > s4 ? s3 : s4) * (size_t)(padded_vecs(n_vec < 16 ? n_vec : 16) + 2);
   return (simt > tc ? simt : tc) * (size_t)n_query * sizeof(float);
 }
 
@@ -462,9 +467,9 @@ int launch_attention_readout(const float* mk, int64_t mk_ch_stride, const float*
   float* part = reinterpret_cast<float*>(workspace);
   if (use_tensor_form(n_mem, n_query)) {
     const float scale2 = 1.4426950408889634f * scale;
-    const int n_splits = pick_splits_tc(n_mem, n_query, n_sm);
     for (int r0 = 0; r0 < n_vec; r0 += 16) {   // 16 mask rows per pass (the softmax state lives in registers)
       const int rows = n_vec - r0 < 16 ? n_vec - r0 : 16;
+      const int n_splits = pick_splits_tc(n_mem, n_query, n_sm, tc_ctas_per_sm(rows));
       const float* v = vec + (int64_t)r0 * vec_row_stride;
       float* o = out + (int64_t)r0 * out_row_stride;
       const int rc = rows <= 4

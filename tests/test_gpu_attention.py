@@ -46,7 +46,8 @@ def test_get_attention_golden(name, form):
 
 @pytest.mark.parametrize("shape,n_vec,scale", [((30, 54), 8, 1.0), ((30, 54), 2, 3.0), ((68, 120), 12, 1.0),
                                                ((5, 7), 33 - 1, 1.0), ((1, 3), 1, 1.0), ((48, 90), 5, 1.5),
-                                               ((12, 20), 3, 2.0e4)])   # beyond fp16 range: the tensor form rescales
+                                               ((12, 20), 3, 2.0e4), ((12, 20), 3, 1.0e-3)])   # beyond fp16 range / deep inside its
+                                                                                           # subnormals: the tensor form normalises
 def test_attention_vs_oracle(shape, n_vec, scale, form):
     """Full sizes (480p: 1620 x 1620; 1080p: 8160 x 8160), ragged tiny grids, up to the 32-row limit."""
     h, w = shape
