@@ -345,6 +345,43 @@ def side_workload(name, args, dev, stream, pk, want_baseline=True):
 
 
 # ----------------------------------------------------------------------------------------------- sharded cfg4
+def attention_workload(dev, stream, pk, steps=20):
+    """The fusion path's attention read (AttentionMemory + get_attention's two vector-matrix products,
+    prop_net.py:117-138, 198-211) at the 480p and the 1080p map, both forms of csrc/attention.cu, against the same ops
+    of the reference in torch on this GPU (oracle.torch_port.attention_lowres: dense HW x HW softmax)."""
+    import evavos_b200 as ev
+    from oracle import torch_port
+    F = torch.nn.functional
+    res = {}
+    for name, (h, w) in (("480p_30x54", (30, 54)), ("1080p_68x120", (68, 120))):
+        g = torch.Generator().manual_seed(h)
+        mk, qk = torch.randn(1, 64, 1, h, w, generator=g).to(dev), torch.randn(1, 64, h, w, generator=g).to(dev)
+        pos = (torch.rand(1, 1, 16 * h, 16 * w, generator=g) > 0.5).float().to(dev)
+        neg = 1 - pos
+        vec = torch.cat([F.interpolate(pos, size=(h, w), mode="area").view(1, -1),
+                         F.interpolate(neg, size=(h, w), mode="area").view(1, -1),
+                         torch.rand(2, h * w, generator=g).to(dev)], 0)          # 4 mask rows: K = 1 (pos / neg per channel)
+        row, old = {"scores": (h * w) ** 2, "mask_rows": 4}, os.environ.get("EVAVOS_ATTENTION_PATH")
+        try:
+            for form in ("simt", "tensor"):
+                os.environ["EVAVOS_ATTENTION_PATH"] = form
+                row[form + "_us"] = 1e3 * time_loop(lambda i: ev.attention_readout(mk, qk, vec), steps, 3, stream, dev) / steps
+                row[form + "_out"] = ev.attention_readout(mk, qk, vec)
+        finally:
+            os.environ.pop("EVAVOS_ATTENTION_PATH", None) if old is None else os.environ.__setitem__("EVAVOS_ATTENTION_PATH", old)
+        row["default_form"] = "tensor" if (h * w) ** 2 >= (1 << 22) else "simt"
+        ref_fn = lambda i: torch_port.attention_lowres(mk, pos, neg, qk)
+        row["torch_us"] = 1e3 * time_loop(ref_fn, 5, 2, stream, dev) / 5
+        want = ref_fn(0).reshape(2, -1)
+        row["max_abs_vs_torch"] = max(float((row.pop(f + "_out")[:2] - want).abs().max()) for f in ("simt", "tensor"))
+        us = row[row["default_form"] + "_us"]
+        row["speedup_vs_torch"] = row["torch_us"] / us
+        row["useful_tflops"] = 2.0 * (h * w) ** 2 * 64 / us / 1e6
+        row["frac_of_bf16_peak"] = row["useful_tflops"] / pk["tc"]
+        res[name] = row
+    return res
+
+
 def run_sharded(args, cfg, rank, world, local_rank, dist=None, emit=True, memory_shards=None):
     """cfg4: one long bank sharded by frame over the ranks; strong scaling (total work fixed).
 
@@ -866,6 +903,10 @@ def run_ours(args, cfg, rank, world, local_rank):
                 line[name] = side_workload(name, args, dev, stream, pk)
             except Exception as e:
                 line[name] = {"error": repr(e)[:300]}
+        try:
+            line["attention_read"] = attention_workload(dev, stream, pk)
+        except Exception as e:
+            line["attention_read"] = {"error": repr(e)[:300]}
     if sharded is not None:
         line["sharded_cfg4"] = sharded
         line["hybrid_cfg4"] = {k_: v_ for k_, v_ in hybrid.items() if v_ is not None}

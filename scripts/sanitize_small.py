@@ -47,5 +47,19 @@ n_over = last_overflow_count()
 pred = torch.rand(3, 37, 53, generator=g).to(dev) > 0.5
 gt = torch.rand(3, 37, 53, generator=g).to(dev) > 0.5
 jf = ev.frame_metrics(pred, gt)
+# round 2, later: the tensor-core form of the attention read (ragged tiles, two split counts, 4 / 8 / 16-row variants)
+# and the decoder's elementwise tails (fp32 and bf16)
+os.environ["EVAVOS_ATTENTION_PATH"] = "tensor"
+for rows in (3, 6, 19):
+    att_tc = ev.attention_readout(mk[:, :, 1:2], qk, torch.rand(rows, H * W, generator=g).to(dev))
+big_k, big_q = torch.randn(1, CK, 1, 20, 27, generator=g).to(dev), torch.randn(1, CK, 20, 27, generator=g).to(dev)
+att_big = ev.attention_readout(big_k, big_q, torch.rand(4, 540, generator=g).to(dev))      # 8.4 tiles over several splits
+os.environ.pop("EVAVOS_ATTENTION_PATH")
+from evavos_b200.decoder_ops import bias_residual_, upsample2x_add_
+for dt in (torch.float32, torch.bfloat16):
+    y = torch.randn(2, 16, 6, 10, generator=g).to(dev, dt).contiguous(memory_format=torch.channels_last)
+    x = torch.randn(2, 16, 3, 5, generator=g).to(dev, dt).contiguous(memory_format=torch.channels_last)
+    bias_residual_(y, torch.randn(16, generator=g).to(dev), y.clone(memory_format=torch.preserve_format), relu=True)
+    upsample2x_add_(y, torch.randn(16, generator=g).to(dev), x)
 torch.cuda.synchronize()
 print("sanitize run ok", float(out.abs().mean()), float(part.abs().mean()), "overflowed queries:", n_over)
