@@ -531,6 +531,8 @@ def run_cfg3(args, cfg, rank, world, local_rank):
     mask = (torch.rand(1, 1, h // 8, (w + 7) // 8, generator=g) > 0.6).float()
     mask = mask.repeat_interleave(8, 2).repeat_interleave(8, 3)[:, :, :h, :w]
 
+    spread = []     # per-video wall-clock spread of every measured engine (the headline `value` is the mean)
+
     def measure(**opts):
         def one_video(i):
             proc = ev.InferenceCore(prop, fuse, videos[i % 2], k, device=dev, **opts)
@@ -538,11 +540,16 @@ def run_cfg3(args, cfg, rank, world, local_rank):
         for i in range(max(2, min(args.warmup, 3))):     # (graph capture, cuDNN autotuning and pinned staging warm up here)
             one_video(i)
         torch.cuda.synchronize(dev)
+        per_video = []
         c0 = time.perf_counter()
         for i in range(args.steps):
-            out = one_video(i)
+            v0 = time.perf_counter()
+            out = one_video(i)                 # (returns host masks: every video ends with a device -> host read)
+            per_video.append(time.perf_counter() - v0)
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - c0
+        spread.append({"opts": opts, "median_ms": 1e3 * sorted(per_video)[len(per_video) // 2], "min_ms": 1e3 * min(per_video),
+                       "max_ms": 1e3 * max(per_video)})
         return world * args.steps * (t - 1) / dt, 1e3 * dt / args.steps, out
 
     # the engine as shipped: fp32 storage, TF32 convolutions (PyTorch's default, i.e. the reference's arithmetic on this
@@ -589,6 +596,7 @@ def run_cfg3(args, cfg, rank, world, local_rank):
         "plain_engine": {"value": plain_fps, "ms_per_step": plain_ms,
                          "note": "fold_bn=False, NCHW, no graphs: PyTorch modules as they are around the same memory read"},
         "gpu_baseline": gpu_base,
+        "per_video_ms": spread,
         "without_fused_decoder_tails": {"value": untail_fps, "ms_per_step": untail_ms},
         "amp_variant": {"value": amp_fps, "ms_per_step": amp_ms, "dtype": "bf16 autocast convolutions (reduced precision: "
                         "not the headline), fp32 keys / values / memory read"},
