@@ -134,3 +134,13 @@ def test_fused_decoder_is_the_same_graph(prop, k, monkeypatch):
     assert fused_decoder(prop) is fused_decoder(prop)               # cached on the network ...
     assert "_evavos_decoder" not in prop.state_dict() and len(prop.state_dict()) == 405
     assert copy.deepcopy(prop).__dict__["_evavos_decoder"].value is None    # ... and not copied with it
+
+
+def test_decoder_tail_kernels_have_no_cpu_path():
+    """evavos_b200.decoder_ops fails loudly on CPU tensors (north_star: no CPU fallback in the product package)."""
+    from evavos_b200.decoder_ops import bias_residual_, upsample2x_add_
+    y = torch.zeros(1, 8, 4, 4).contiguous(memory_format=torch.channels_last)
+    with pytest.raises(RuntimeError, match="CUDA tensor required"):
+        bias_residual_(y, torch.zeros(8))
+    with pytest.raises(RuntimeError, match="CUDA tensor required"):
+        upsample2x_add_(y, torch.zeros(8), torch.zeros(1, 8, 2, 2).contiguous(memory_format=torch.channels_last))
