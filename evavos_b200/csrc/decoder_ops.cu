@@ -70,36 +70,42 @@ __global__ void __launch_bounds__(256) bias_residual_kernel(T* __restrict__ y, c
   }
 }
 
-// y: (n, H, W, C); x: (n, H/2, W/2, C); y += bias + up2x(x).
+// y: (n, H, W, C); x: (n, H/2, W/2, C); y += bias + up2x(x).  grid (n * H, splits): a CTA owns a slice of ONE output row,
+// so the row's two source rows and vertical weights are CTA constants and a vector index needs one 32-bit division.
+// (A flat grid-stride loop that takes a 64-bit vector index apart - five emulated divisions - ran at 0.61 of the HBM
+// roofline with the issue slots 65 % busy; 32-bit indices: 0.70.)
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_add_kernel(T* __restrict__ y, const float* __restrict__ bias,
-                                                             const T* __restrict__ x, int64_t n_vec, int c_vecs, int H,
-                                                             int W) {
+                                                             const T* __restrict__ x, int c_vecs, int H, int W) {
   constexpr int N = Vec<T>::N;
   const int h2 = H >> 1, w2 = W >> 1;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % c_vecs);
-    int64_t p = i / c_vecs;
-    const int wo = (int)(p % W);
-    p /= W;
-    const int ho = (int)(p % H);
-    const int64_t n = p / H;
-    // ATen: src = max((dst + 0.5) * 0.5 - 0.5, 0); i0 = floor(src); i1 = min(i0 + 1, size - 1); l1 = src - i0; l0 = 1 - l1
-    const float sh = fmaxf((ho + 0.5f) * 0.5f - 0.5f, 0.f), sw = fmaxf((wo + 0.5f) * 0.5f - 0.5f, 0.f);
-    const int h0 = (int)sh, w0 = (int)sw;
-    const int h1 = min(h0 + 1, h2 - 1), w1 = min(w0 + 1, w2 - 1);
-    const float lh1 = sh - (float)h0, lw1 = sw - (float)w0;
-    const float lh0 = 1.f - lh1, lw0 = 1.f - lw1;
-    const T* xb = x + (n * h2 * w2) * (int64_t)c_vecs * N + cv * N;
+  const int row = blockIdx.x, n = row / H, ho = row - n * H;
+  // ATen: src = max((dst + 0.5) * 0.5 - 0.5, 0); i0 = floor(src); i1 = min(i0 + 1, size - 1); l1 = src - i0; l0 = 1 - l1
+  const float sh = fmaxf((ho + 0.5f) * 0.5f - 0.5f, 0.f);
+  const int h0 = (int)sh, h1 = min(h0 + 1, h2 - 1);
+  const float lh1 = sh - (float)h0, lh0 = 1.f - lh1;
+  const int wa = (int)(((int64_t)W * blockIdx.y) / gridDim.y), wb = (int)(((int64_t)W * (blockIdx.y + 1)) / gridDim.y);
+  const int64_t src_row = (int64_t)w2 * c_vecs * N;
+  const T* x0 = x + ((int64_t)n * h2 + h0) * src_row;
+  const T* x1 = x + ((int64_t)n * h2 + h1) * src_row;
+  T* yr = y + (int64_t)row * W * c_vecs * N;
+  const int n_items = (wb - wa) * c_vecs;
+  for (int e = threadIdx.x; e < n_items; e += 256) {
+    const int wq = e / c_vecs, co = (e - wq * c_vecs) * N, wo = wa + wq;
+    const float sw = fmaxf((wo + 0.5f) * 0.5f - 0.5f, 0.f);
+    const int w0 = (int)sw, w1 = min(w0 + 1, w2 - 1);
+    const float lw1 = sw - (float)w0, lw0 = 1.f - lw1;
+    const int o0 = w0 * c_vecs * N + co, o1 = w1 * c_vecs * N + co;
+    T* yp = yr + (int64_t)wo * c_vecs * N + co;
     float a00[N], a01[N], a10[N], a11[N], v[N], b[N];
-    Vec<T>::load(xb + ((int64_t)h0 * w2 + w0) * c_vecs * N, a00);
-    Vec<T>::load(xb + ((int64_t)h0 * w2 + w1) * c_vecs * N, a01);
-    Vec<T>::load(xb + ((int64_t)h1 * w2 + w0) * c_vecs * N, a10);
-    Vec<T>::load(xb + ((int64_t)h1 * w2 + w1) * c_vecs * N, a11);
-    Vec<T>::load(y + i * N, v);
+    Vec<T>::load(x0 + o0, a00);
+    Vec<T>::load(x0 + o1, a01);
+    Vec<T>::load(x1 + o0, a10);
+    Vec<T>::load(x1 + o1, a11);
+    Vec<T>::load(yp, v);
 #pragma unroll
     for (int j = 0; j < N; j += 4) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(bias + cv * N + j));
+      const float4 q = __ldg(reinterpret_cast<const float4*>(bias + co + j));
       b[j] = q.x; b[j + 1] = q.y; b[j + 2] = q.z; b[j + 3] = q.w;
     }
 #pragma unroll
@@ -107,7 +113,7 @@ __global__ void __launch_bounds__(256) upsample2x_add_kernel(T* __restrict__ y, 
       const float up = lh0 * (lw0 * a00[j] + lw1 * a01[j]) + lh1 * (lw0 * a10[j] + lw1 * a11[j]);
       v[j] = (v[j] + b[j]) + up;
     }
-    Vec<T>::store(y + i * N, v);
+    Vec<T>::store(yp, v);
   }
 }
 
@@ -134,17 +140,21 @@ int launch_bias_residual(void* y, const float* bias, const void* r, int64_t rows
   return EVAVOS_OK;
 }
 
+template <typename T>
+static void launch_up(T* y, const float* bias, const T* x, int64_t n, int cv, int H, int W, cudaStream_t st) {
+  const int64_t rows = n * H;
+  int64_t splits = ceil_div(148 * 32, rows);    // ~4 waves of 8 CTAs per SM (two CTAs more than one wave cost a whole second one)
+  if (splits > W) splits = W;
+  if (splits > 65535) splits = 65535;
+  if (splits < 1) splits = 1;
+  upsample2x_add_kernel<T><<<dim3((unsigned)rows, (unsigned)splits), 256, 0, st>>>(y, bias, x, cv, H, W);
+}
+
 int launch_upsample2x_add(void* y, const float* bias, const void* x, int64_t n, int H, int W, int C, int bf16, cudaStream_t st) {
   if (n <= 0) return EVAVOS_OK;
-  if (bf16) {
-    const int cv = C / 8;
-    upsample2x_add_kernel<__nv_bfloat16><<<grid_for(n * H * W * cv), 256, 0, st>>>(
-        reinterpret_cast<__nv_bfloat16*>(y), bias, reinterpret_cast<const __nv_bfloat16*>(x), n * H * W * cv, cv, H, W);
-  } else {
-    const int cv = C / 4;
-    upsample2x_add_kernel<float><<<grid_for(n * H * W * cv), 256, 0, st>>>(
-        reinterpret_cast<float*>(y), bias, reinterpret_cast<const float*>(x), n * H * W * cv, cv, H, W);
-  }
+  if (n * H > 0x7fffffffll || (int64_t)W * C > 0x3fffffffll) return EVAVOS_ERR_INVALID;
+  if (bf16) launch_up(reinterpret_cast<__nv_bfloat16*>(y), bias, reinterpret_cast<const __nv_bfloat16*>(x), n, C / 8, H, W, st);
+  else launch_up(reinterpret_cast<float*>(y), bias, reinterpret_cast<const float*>(x), n, C / 4, H, W, st);
   EVAVOS_CUDA_OK(cudaGetLastError());
   return EVAVOS_OK;
 }
