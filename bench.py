@@ -23,7 +23,11 @@ ONE JSON line:
               `e2e_full_upload` is the stateless evavos_memread_host form.
  * cpu_baseline / --impl reference   oracle/torch_port.py on all host cores (/root/reference is not on the GPU box).
  * N == 1 also carries `cfg4` and `cfg5`: BASELINE.json configs[3] (unsharded, one GPU) and configs[4] (bf16 values)
-   with their own stage times, rooflines and GPU baselines.
+   with their own stage times, rooflines and GPU baselines; and `attention_read`: the fusion path's attention read
+    at the 480p and 1080p maps, both forms of csrc/attention.cu, beside the reference's torch ops.
+ * --workload cfg3: `InferenceCore.interact` end to end (frames/s of the default engine, the plain engine, the bf16
+   variant, the engine without the fused decoder tails, per-video median / min / max), and `gpu_baseline`: the
+   reference's stock propagation loop (oracle/stock_engine.py) on the same GPU with the mask agreement between the two.
  * N > 1: ranks run independent videos (no collective, weak scaling: the headline line), and the line also carries
    `sharded_cfg4`: ONE 200-frame bank sharded along the memory axis over the N ranks (device-initiated exchange over
    NVLink peer memory; EVAVOS_SHARD_EXCHANGE=nccl for the library baseline) with per-rank stage times, the same run's
